@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Build libquiver_b200.so (sm_100a only) next to the Python adapter.  Usage: csrc/build.sh [extra nvcc flags]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+ROOT="$(cd "$HERE/../.." && pwd)"
+OUT="$HERE/../torch_quiver/libquiver_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+mkdir -p "$HERE/build"
+objs=()
+for f in qv_runtime qv_xorwow qv_sample qv_gather; do
+  src="$HERE/$f.cu"; obj="$HERE/build/$f.o"
+  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/qv_common.cuh" -nt "$obj" || "$HERE/qv_xorwow.cuh" -nt "$obj" || "$ROOT/include/quiver_b200.h" -nt "$obj" ]]; then
+    "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden \
+      -I"$ROOT/include" "$@" -c "$src" -o "$obj" &
+  fi
+  objs+=("$obj")
+done
+wait
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC "${objs[@]}" -o "$OUT" -lpthread -ldl -lrt
+echo "built $OUT"

@@ -1,0 +1,399 @@
+// qv_gather.cu -- tiered / sharded feature gather ("collect") for B200 (sm_100a).
+//
+// Replaces quiver_tensor_gather + find (srcs/cpp/include/quiver/shard_tensor.cu.hpp:7-61) as launched by
+// ShardTensor::operator[] (srcs/cpp/src/quiver/cuda/quiver_feature.cu:246-302), and folds in the
+// feature_order[idx] indirection of Feature.__getitem__ (srcs/python/quiver/feature.py:300-301).
+//
+// The reference moves ONE BYTE per lane per instruction (32 B per warp instruction) and re-reads the shard offset
+// table from global memory for every row.  Here:
+//   * the shard table (<= 16 entries) travels in the kernel parameters (__grid_constant__, constant bank reads);
+//   * variant 1 (SIMT): the output is treated as a flat array of 16-byte chunks; a thread moves `kUnroll` chunks with
+//     all loads issued before the first store (MLP), 128-bit streaming loads from whichever tier owns the row
+//     (local HBM / peer HBM over NVLink / pinned host over PCIe -- the pointer decides) and perfectly coalesced
+//     128-bit streaming stores.  Rows whose size is not a multiple of 16 fall back to 8/4/2/1-byte chunks;
+//   * variant 2 (TMA): rows are pulled with cp.async.bulk (one bulk copy per row, issued by single lanes, completion
+//     on an mbarrier) into a shared-memory ring and pushed out with ONE bulk store per stage, because consecutive
+//     output rows are contiguous.  No registers touch the payload.  Needs row_bytes % 16 == 0.
+//   * ids outside [0, rows) and inaccessible shards produce zero rows (the reference leaves them uninitialised).
+#include <algorithm>
+
+#include "qv_common.cuh"
+
+namespace qv
+{
+namespace
+{
+struct GatherParams {
+    int32_t n_shards;
+    int32_t _pad;
+    int64_t row_begin[QV_MAX_SHARDS + 1];
+    const char *ptr[QV_MAX_SHARDS];  // nullptr = not accessible from this device
+    int64_t pitch[QV_MAX_SHARDS];
+};
+
+// Source address of logical row `id`, or nullptr for "zero row".
+__device__ __forceinline__ const char *row_source(const GatherParams &t, int64_t id)
+{
+    if (id < 0 || id >= t.row_begin[t.n_shards]) return nullptr;
+    int s = 0;
+#pragma unroll 4
+    for (int i = 1; i < QV_MAX_SHARDS; i++)
+        if (i < t.n_shards && id >= t.row_begin[i]) s = i;
+    const char *base = t.ptr[s];
+    return base ? base + (id - t.row_begin[s]) * t.pitch[s] : nullptr;
+}
+
+__device__ __forceinline__ int64_t logical_row(const int64_t *__restrict__ indices,
+                                               const int64_t *__restrict__ feature_order, int64_t n_rows_total,
+                                               int64_t i)
+{
+    int64_t id = indices[i];
+    if (feature_order) id = (id >= 0 && id < n_rows_total) ? feature_order[id] : -1;
+    return id;
+}
+
+template <int kBytes>
+struct Chunk;
+template <>
+struct Chunk<16> {
+    using T = int4;
+    static __device__ __forceinline__ T load(const char *p) { return ld_stream_v4(p); }
+    static __device__ __forceinline__ void store(char *p, const T &v) { st_stream_v4(p, v); }
+    static __device__ __forceinline__ T zero() { return make_int4(0, 0, 0, 0); }
+};
+template <>
+struct Chunk<8> {
+    using T = int2;
+    static __device__ __forceinline__ T load(const char *p) { return ld_stream_v2(p); }
+    static __device__ __forceinline__ void store(char *p, const T &v) { st_stream_v2(p, v); }
+    static __device__ __forceinline__ T zero() { return make_int2(0, 0); }
+};
+template <>
+struct Chunk<4> {
+    using T = int;
+    static __device__ __forceinline__ T load(const char *p) { return __ldg(reinterpret_cast<const int *>(p)); }
+    static __device__ __forceinline__ void store(char *p, const T &v) { *reinterpret_cast<int *>(p) = v; }
+    static __device__ __forceinline__ T zero() { return 0; }
+};
+template <>
+struct Chunk<2> {
+    using T = short;
+    static __device__ __forceinline__ T load(const char *p) { return __ldg(reinterpret_cast<const short *>(p)); }
+    static __device__ __forceinline__ void store(char *p, const T &v) { *reinterpret_cast<short *>(p) = v; }
+    static __device__ __forceinline__ T zero() { return 0; }
+};
+template <>
+struct Chunk<1> {
+    using T = char;
+    static __device__ __forceinline__ T load(const char *p) { return __ldg(p); }
+    static __device__ __forceinline__ void store(char *p, const T &v) { *p = v; }
+    static __device__ __forceinline__ T zero() { return 0; }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant 1: flat chunked SIMT gather.
+// Block = kThreads threads, each block owns kThreads*kUnroll consecutive output chunks.  chunks_per_row (cpr) and the
+// multiplier inv = floor(2^32/cpr)+1 give an exact 32-bit division for the block-local chunk offset (< cpr + tile).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGatherThreads = 256;
+constexpr int kGatherUnroll = 4;
+
+template <int kBytes>
+__global__ void __launch_bounds__(kGatherThreads)
+    gather_flat_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
+                       const int64_t *__restrict__ feature_order, int64_t n, uint32_t cpr, uint32_t inv,
+                       char *__restrict__ out)
+{
+    using C = Chunk<kBytes>;
+    constexpr uint32_t kTile = kGatherThreads * kGatherUnroll;
+    const int64_t total_chunks = n * static_cast<int64_t>(cpr);
+    const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * kTile;
+    // first row of the tile and the tile's chunk offset inside that row (one 64-bit division per thread)
+    const int64_t row0 = tile_base / cpr;
+    const uint32_t off0 = static_cast<uint32_t>(tile_base - row0 * cpr);
+    const int64_t n_rows_total = t.row_begin[t.n_shards];
+
+    typename C::T v[kGatherUnroll];
+    const char *src[kGatherUnroll];
+    bool live[kGatherUnroll];
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) {
+        const uint32_t local = threadIdx.x + u * kGatherThreads;
+        live[u] = tile_base + local < total_chunks;
+        src[u] = nullptr;
+        if (live[u]) {
+            const uint32_t l = off0 + local;
+            const uint32_t dr = cpr == 1 ? l : __umulhi(l, inv);  // exact: l * cpr < 2^32 (checked by the host)
+            const uint32_t col = l - dr * cpr;
+            const int64_t id = logical_row(indices, feature_order, n_rows_total, row0 + dr);
+            const char *base = row_source(t, id);
+            if (base) src[u] = base + static_cast<size_t>(col) * kBytes;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) v[u] = src[u] ? C::load(src[u]) : C::zero();
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) {
+        if (live[u]) {
+            const int64_t c = tile_base + threadIdx.x + u * kGatherThreads;
+            C::store(out + c * kBytes, v[u]);
+        }
+    }
+}
+
+// Fallback for rows too long for the 32-bit trick: one warp per row, 64-bit addressing.
+template <int kBytes>
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
+                       const int64_t *__restrict__ feature_order, int64_t n, int64_t cpr, char *__restrict__ out)
+{
+    using C = Chunk<kBytes>;
+    const int64_t n_rows_total = t.row_begin[t.n_shards];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < n; r += n_warps) {
+        const char *base = row_source(t, logical_row(indices, feature_order, n_rows_total, r));
+        char *dst = out + r * cpr * kBytes;
+        for (int64_t c = lane; c < cpr; c += 32) C::store(dst + c * kBytes, base ? C::load(base + c * kBytes) : C::zero());
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant 2: TMA bulk-copy pipeline.  One CTA = one producer warp; a stage holds kRowsPerStage consecutive output
+// rows.  Lane l issues the bulk load of row l of the stage (global -> shared, completes on the stage's mbarrier);
+// when the barrier flips, lane 0 issues one bulk store of the whole stage (shared -> global) and the ring advances.
+// Zero rows are written into shared memory by the lanes themselves.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_addr(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kKeep>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kKeep) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(32)
+    gather_tma_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
+                      const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, int rows_per_stage,
+                      char *__restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kTmaStages];
+    const int lane = threadIdx.x;
+    const uint32_t stage_bytes = row_bytes * rows_per_stage;
+    const int64_t n_rows_total = t.row_begin[t.n_shards];
+    if (lane == 0) {
+        for (int s = 0; s < kTmaStages; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int64_t n_groups = (n + rows_per_stage - 1) / rows_per_stage;
+    // this CTA handles groups blockIdx.x, blockIdx.x + gridDim.x, ...
+    int64_t issue = blockIdx.x;  // next group to load
+    int64_t drain = blockIdx.x;  // next group to store
+    int issue_slot = 0, drain_slot = 0;
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+
+    auto issue_group = [&](int64_t g, int slot) {
+        unsigned char *stage = smem_raw + static_cast<size_t>(slot) * stage_bytes;
+        const int64_t first = g * rows_per_stage;
+        const int rows = static_cast<int>(min(static_cast<int64_t>(rows_per_stage), n - first));
+        // expected bytes = rows that really come from memory; zero rows are filled by hand
+        uint32_t tx = 0;
+        const char *src[4];
+        for (int it = 0; it * 32 < rows_per_stage; it++) {
+            const int r = lane + it * 32;
+            src[it] = nullptr;
+            if (r < rows) src[it] = row_source(t, logical_row(indices, feature_order, n_rows_total, first + r));
+            tx += __popc(__ballot_sync(0xffffffffu, src[it] != nullptr)) * row_bytes;
+            if (r < rows && src[it] == nullptr) {
+                int4 *z = reinterpret_cast<int4 *>(stage + static_cast<size_t>(r) * row_bytes);
+                for (uint32_t c = 0; c < row_bytes / 16; c++) z[c] = make_int4(0, 0, 0, 0);
+            }
+        }
+        fence_proxy_async();  // hand-written zero rows must be visible to the bulk store
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&full[slot], tx);
+        __syncwarp();
+        for (int it = 0; it * 32 < rows_per_stage; it++) {
+            const int r = lane + it * 32;
+            if (src[it]) bulk_load(stage + static_cast<size_t>(r) * row_bytes, src[it], row_bytes, &full[slot]);
+        }
+    };
+
+    // prologue: fill the ring
+    for (int s = 0; s < kTmaStages && issue < n_groups; s++) {
+        issue_group(issue, issue_slot);
+        issue += gridDim.x;
+        issue_slot = (issue_slot + 1) % kTmaStages;
+    }
+    while (drain < n_groups) {
+        mbar_wait(&full[drain_slot], (phase_bits >> drain_slot) & 1u);
+        phase_bits ^= 1u << drain_slot;
+        const int64_t first = drain * rows_per_stage;
+        const int rows = static_cast<int>(min(static_cast<int64_t>(rows_per_stage), n - first));
+        if (lane == 0) {
+            bulk_store(out + first * row_bytes, smem_raw + static_cast<size_t>(drain_slot) * stage_bytes,
+                       static_cast<uint32_t>(rows) * row_bytes);
+            bulk_commit();
+        }
+        drain += gridDim.x;
+        // refill this slot once its store has finished READING shared memory
+        if (issue < n_groups) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+            issue_group(issue, drain_slot);
+            issue += gridDim.x;
+        }
+        drain_slot = (drain_slot + 1) % kTmaStages;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+    (void)issue_slot;
+}
+
+inline int pick_chunk(int64_t row_bytes, const qv_shard_table *tab, const void *out)
+{
+    uintptr_t bits = static_cast<uintptr_t>(row_bytes) | reinterpret_cast<uintptr_t>(out);
+    for (int s = 0; s < tab->n_shards; s++) {
+        bits |= reinterpret_cast<uintptr_t>(tab->ptr[s]);
+        bits |= static_cast<uintptr_t>(tab->pitch[s]);
+    }
+    if ((bits & 15) == 0) return 16;
+    if ((bits & 7) == 0) return 8;
+    if ((bits & 3) == 0) return 4;
+    if ((bits & 1) == 0) return 2;
+    return 1;
+}
+
+template <int kBytes>
+int launch_simt(const GatherParams &p, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                int64_t row_bytes, char *out, int n_sm, cudaStream_t st)
+{
+    const int64_t cpr = row_bytes / kBytes;
+    constexpr int64_t kTile = kGatherThreads * kGatherUnroll;
+    const int64_t total = n * cpr;
+    const int64_t blocks = (total + kTile - 1) / kTile;
+    // exactness of the __umulhi division needs (cpr + tile) * cpr < 2^32
+    if ((cpr + kTile) * cpr < (int64_t(1) << 32) && blocks < (int64_t(1) << 31)) {
+        const uint32_t inv = static_cast<uint32_t>((uint64_t(1) << 32) / static_cast<uint64_t>(cpr)) + 1u;
+        gather_flat_kernel<kBytes><<<static_cast<unsigned>(blocks), kGatherThreads, 0, st>>>(
+            p, indices, feature_order, n, static_cast<uint32_t>(cpr), cpr == 1 ? 0u : inv, out);
+        QV_CHECK_LAUNCH("gather_flat_kernel");
+    } else {
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, int64_t(n_sm) * 16));
+        gather_rows_kernel<kBytes><<<grid, 256, 0, st>>>(p, indices, feature_order, n, cpr, out);
+        QV_CHECK_LAUNCH("gather_rows_kernel");
+    }
+    return QV_OK;
+}
+}  // namespace
+}  // namespace qv
+
+using namespace qv;
+
+extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                         int64_t row_bytes, void *out, int variant, qv_stream_t stream)
+{
+    QV_REQUIRE(table != nullptr, "qv_gather: table is NULL");
+    QV_REQUIRE(table->n_shards >= 1 && table->n_shards <= QV_MAX_SHARDS, "qv_gather: n_shards = %d outside [1, %d]",
+               table->n_shards, QV_MAX_SHARDS);
+    QV_REQUIRE(n >= 0 && row_bytes > 0, "qv_gather: bad sizes (n = %lld, row_bytes = %lld)", (long long)n,
+               (long long)row_bytes);
+    if (n == 0) return QV_OK;
+    QV_REQUIRE(indices && out, "qv_gather: NULL array");
+    GatherParams p;
+    memset(&p, 0, sizeof p);
+    p.n_shards = table->n_shards;
+    QV_REQUIRE(table->row_begin[0] == 0, "qv_gather: row_begin[0] must be 0");
+    for (int s = 0; s < table->n_shards; s++) {
+        QV_REQUIRE(table->row_begin[s + 1] >= table->row_begin[s], "qv_gather: row_begin not monotone at shard %d", s);
+        QV_REQUIRE(table->pitch[s] >= row_bytes || table->row_begin[s + 1] == table->row_begin[s],
+                   "qv_gather: shard %d pitch %lld < row_bytes %lld", s, (long long)table->pitch[s],
+                   (long long)row_bytes);
+        p.row_begin[s] = table->row_begin[s];
+        p.ptr[s] = (table->accessible[s] && table->ptr[s]) ? static_cast<const char *>(table->ptr[s]) : nullptr;
+        p.pitch[s] = table->pitch[s];
+    }
+    for (int s = table->n_shards; s <= QV_MAX_SHARDS; s++) p.row_begin[s] = table->row_begin[table->n_shards];
+    p.row_begin[table->n_shards] = table->row_begin[table->n_shards];
+
+    int device = 0;
+    QV_CUDA(cudaGetDevice(&device));
+    const int n_sm = sm_count(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *o = static_cast<char *>(out);
+    const int chunk = pick_chunk(row_bytes, table, out);
+
+    if (variant == 2 || (variant == 0 && false)) {
+        QV_REQUIRE(chunk == 16, "qv_gather: the TMA variant needs 16-byte aligned rows, pitches and pointers");
+        QV_REQUIRE(row_bytes <= 48 * 1024, "qv_gather: the TMA variant supports rows up to 48 KiB");
+        // stage = up to 32 rows, <= 48 KiB; 4 stages
+        int rows_per_stage = static_cast<int>(std::min<int64_t>(32, (48 * 1024) / row_bytes));
+        rows_per_stage = std::max(rows_per_stage, 1);
+        const size_t smem = static_cast<size_t>(kTmaStages) * rows_per_stage * row_bytes;
+        static bool attr_set[64] = {false};
+        if (device < 0 || device >= 64 || !attr_set[device]) {
+            QV_CUDA(cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            if (device >= 0 && device < 64) attr_set[device] = true;
+        }
+        const int64_t n_groups = (n + rows_per_stage - 1) / rows_per_stage;
+        const int ctas_per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smem + 1024))));
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_groups, int64_t(n_sm) * ctas_per_sm));
+        gather_tma_kernel<<<grid, 32, smem, st>>>(p, indices, feature_order, n, static_cast<uint32_t>(row_bytes),
+                                                   rows_per_stage, o);
+        QV_CHECK_LAUNCH("gather_tma_kernel");
+        return QV_OK;
+    }
+    switch (chunk) {
+    case 16:
+        return launch_simt<16>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+    case 8:
+        return launch_simt<8>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+    case 4:
+        return launch_simt<4>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+    case 2:
+        return launch_simt<2>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+    default:
+        return launch_simt<1>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+    }
+}

@@ -1,0 +1,867 @@
+// qv_sample.cu -- CSR k-hop neighbour sampler for B200 (sm_100a): count+scan, row-wise reservoir sampling with the
+// reference's exact XORWOW work decomposition, ordered-hash reindex, and the fused k-hop driver.
+//
+// What it replaces (reference file:line):
+//   TorchQuiver::sample_neighbor / sample_kernel        srcs/cpp/src/quiver/cuda/quiver_sample.cu:113-200
+//   CSRRowWiseSampleKernel                              srcs/cpp/include/quiver/cuda_random.cu.hpp:7-69
+//   TorchQuiver::reindex_single / reindex_kernel        quiver_sample.cu:305-357, 202-255, FillWithDuplicates :18-63
+//   DeviceOrderedHashTable                              srcs/cpp/include/quiver/reindex.cu.hpp:20-158
+//   GraphSageSampler.sample's hop loop                  srcs/python/quiver/pyg/sage_sampler.py:118-147
+//   cal_next                                            cuda_random.cu.hpp:71-104
+//
+// Design (B200-first, not a translation):
+//   * no per-call cudaMalloc / cudaMemset / thrust: one sampler-owned scratch arena, everything stream-ordered on the
+//     caller's stream (the reference uses a private stream pool and ~10 blocking allocations per hop);
+//   * every kernel takes its problem size from DEVICE memory, so all hops of a k-hop sample are enqueued back to back
+//     and the host synchronises exactly once;
+//   * prefix sums are single-pass chained scans (decoupled look-back) fused with the work that produces their input
+//     (degree/cap for the sampler, "is first occurrence" for the reindex);
+//   * XORWOW states come from a cache (qv_xorwow.cuh) instead of a per-thread skip-ahead every launch;
+//   * reservoir slots live in shared memory (32-bit), row metadata for a warp's 16 rows is fetched in one wave;
+//   * int64 ids and 64-bit sizes throughout (the reference truncates to int in several places).
+#include <algorithm>
+#include <new>
+
+#include "qv_common.cuh"
+#include "qv_xorwow.cuh"
+
+namespace qv
+{
+namespace
+{
+// ------------------------------------------------------------------------------------------------------------------
+// Device-resident sizes.  meta[kMetaStride*h + ...] for hop h.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMetaS = 0;  // number of seeds of the hop
+constexpr int kMetaE = 1;  // number of sampled edges (sum of counts)
+constexpr int kMetaF = 2;  // frontier size after reindex
+constexpr int kMetaStride = 4;
+constexpr int kMetaWords = kMetaStride * (QV_MAX_HOPS + 1);
+
+__device__ __forceinline__ int64_t dev_size(int64_t arg, const int64_t *d)
+{
+    return d ? *d : arg;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-pass chained scan (decoupled look-back).  Tile descriptors: bits 63..62 = flag, 61..0 = value.
+// Tiles take their index from an atomic ticket so a tile only ever waits on tiles that are already running.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagPrefix = 2ull << 62;
+constexpr unsigned long long kValueMask = (1ull << 62) - 1;
+
+struct ScanState {
+    unsigned long long *words;  // [0] = ticket, [1 + tile] = descriptor; zeroed before each launch
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ long long warp_sum_i64(long long v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Returns the exclusive prefix of this thread's `thread_sum` over the whole grid; `tile` is the ticketed tile index.
+// Must be called by all kScanThreads threads.  The last tile stores the grand total to *d_total.
+__device__ __forceinline__ long long chained_scan(long long thread_sum, ScanState st, int tile, int n_tiles,
+                                                  int64_t *d_total)
+{
+    __shared__ long long warp_tot[kScanThreads / 32];
+    __shared__ long long tile_excl_sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    long long incl = thread_sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+
+    long long warp_base = 0, block_agg = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) {
+        const long long t = warp_tot[w];
+        if (w < warp) warp_base += t;
+        block_agg += t;
+    }
+
+    if (warp == 0) {
+        unsigned long long *desc = st.words + 1;
+        long long excl = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(desc, kFlagPrefix | (static_cast<unsigned long long>(block_agg) & kValueMask));
+        } else {
+            if (lane == 0)
+                st_volatile_u64(desc + tile, kFlagAgg | (static_cast<unsigned long long>(block_agg) & kValueMask));
+            long long run = 0;
+            int look = tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long w = (idx >= 0) ? ld_volatile_u64(desc + idx) : kFlagPrefix;
+                while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+                    if ((w >> 62) == 0) w = ld_volatile_u64(desc + idx);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                const long long val = static_cast<long long>(w & kValueMask);
+                if (pm) {
+                    const int first = __ffs(pm) - 1;
+                    run += warp_sum_i64(lane <= first ? val : 0);
+                    break;
+                }
+                run += warp_sum_i64(val);
+                look -= 32;
+            }
+            excl = run;
+            if (lane == 0)
+                st_volatile_u64(desc + tile,
+                                kFlagPrefix | (static_cast<unsigned long long>(run + block_agg) & kValueMask));
+        }
+        if (lane == 0) {
+            tile_excl_sh = excl;
+            if (tile == n_tiles - 1 && d_total) *d_total = excl + block_agg;
+        }
+    }
+    __syncthreads();
+    return tile_excl_sh + warp_base + (incl - thread_sum);
+}
+
+__device__ __forceinline__ int take_ticket(ScanState st)
+{
+    __shared__ int tile_sh;
+    if (threadIdx.x == 0) tile_sh = static_cast<int>(atomicAdd(st.words, 1ull));
+    __syncthreads();
+    return tile_sh;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel A: counts[i] = min(deg(seed_i), k), out_ptr = exclusive scan, total.   (quiver_sample.cu:157-169)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads)
+    count_scan_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, const int64_t *__restrict__ seeds,
+                      int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k, int64_t *__restrict__ counts,
+                      int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles)
+{
+    const int64_t S = dev_size(S_arg, d_S);
+    const int tile = take_ticket(st);
+    const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
+    long long c[kScanItems];
+    long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        long long v = 0;
+        if (i < S) {
+            const int64_t node = seeds[i];
+            if (node >= 0 && node < n_nodes) {
+                const int64_t deg = indptr[node + 1] - indptr[node];
+                v = (k >= 0 && deg > k) ? k : deg;
+            }
+        }
+        c[j] = v;
+        sum += v;
+    }
+    long long excl = chained_scan(sum, st, tile, n_tiles, d_total);
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        if (i < S) {
+            if (counts) counts[i] = c[j];
+            out_ptr[i] = excl;
+        }
+        excl += c[j];
+    }
+}
+
+// Plain exclusive scan of an int64 array (reindex_single's exclusive_scan(count), quiver_sample.cu:321).
+__global__ void __launch_bounds__(kScanThreads)
+    plain_scan_kernel(const int64_t *__restrict__ in, int64_t n, int64_t *__restrict__ out, int64_t *__restrict__ d_total,
+                      ScanState st, int n_tiles)
+{
+    const int tile = take_ticket(st);
+    const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
+    long long c[kScanItems];
+    long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        c[j] = (i < n) ? in[i] : 0;
+        sum += c[j];
+    }
+    long long excl = chained_scan(sum, st, tile, n_tiles, d_total);
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        if (i < n) out[i] = excl;
+        excl += c[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kernel B: row-wise sampling with the reference's generator assignment.
+//   virtual block b = 64 consecutive seeds; warp w of the block owns seeds 64b+w, 64b+w+4, ... (<= 16 of them) and its
+//   32 lanes own XORWOW streams (seed rand_seed*grid+b, sub-sequence 32w+lane) that persist across those seeds
+//   (cuda_random.cu.hpp:17-25,67).  deg <= k: verbatim copy (:33-38).  deg > k: reservoir over positions with
+//   max-wins slots (:41-57) then gather (:61-64).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kSampleWarps = 4;
+constexpr int kSampleTile = 64;
+constexpr int kRowsPerWarp = kSampleTile / kSampleWarps;  // 16
+constexpr int kSmemSlots = 1024;                          // per warp; larger fan-outs use the output row as slots
+
+template <bool kSlotsInSmem>
+__global__ void __launch_bounds__(kSampleWarps * 32)
+    sample_rows_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
+                       const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k_arg,
+                       const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
+                       int64_t *__restrict__ out, int64_t *__restrict__ row_out, const int64_t *__restrict__ d_row_off)
+{
+    __shared__ uint32_t slots_sh[kSlotsInSmem ? kSampleWarps * kSmemSlots : 1];
+    const int64_t S = dev_size(S_arg, d_S);
+    const int64_t b = blockIdx.x;
+    if (b * kSampleTile >= S) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = k_arg < 0 ? INT64_MAX : k_arg;
+
+    Xorwow rng;
+    {
+        const uint32_t *p = rng_states + static_cast<size_t>(b) * kRngStateWords * kRngBlockThreads + threadIdx.x;
+        rng.d = p[0 * kRngBlockThreads];
+        rng.v0 = p[1 * kRngBlockThreads];
+        rng.v1 = p[2 * kRngBlockThreads];
+        rng.v2 = p[3 * kRngBlockThreads];
+        rng.v3 = p[4 * kRngBlockThreads];
+        rng.v4 = p[5 * kRngBlockThreads];
+    }
+
+    // one wave of loads fetches the metadata of all (<= 16) rows this warp owns: lane i holds row i
+    int64_t my_start = 0, my_deg = 0, my_o = 0;
+    {
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
+        if (lane < kRowsPerWarp && r < S) {
+            const int64_t node = seeds[r];
+            my_o = out_ptr[r];
+            if (node >= 0 && node < n_nodes) {
+                my_start = indptr[node];
+                my_deg = indptr[node + 1] - my_start;
+            }
+        }
+    }
+    const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
+    uint32_t *slots = slots_sh + (kSlotsInSmem ? w * kSmemSlots : 0);
+
+    for (int i = 0; i < kRowsPerWarp; i++) {
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
+        if (r >= S) break;
+        const int64_t start = __shfl_sync(0xffffffffu, my_start, i);
+        const int64_t deg = __shfl_sync(0xffffffffu, my_deg, i);
+        const int64_t o = __shfl_sync(0xffffffffu, my_o, i);
+        const int64_t cnt = deg <= k ? deg : k;
+        if (row_out)
+            for (int64_t j = lane; j < cnt; j += 32) row_out[row_off + o + j] = r;
+        if (deg <= k) {
+            for (int64_t j = lane; j < deg; j += 32) out[o + j] = indices[start + j];
+        } else if (kSlotsInSmem) {
+            const uint32_t kk = static_cast<uint32_t>(k);
+            for (uint32_t j = lane; j < kk; j += 32) slots[j] = j;
+            __syncwarp();
+            for (int64_t idx = k + lane; idx < deg; idx += 32) {
+                const uint32_t num = xorwow_next(rng) % static_cast<uint32_t>(idx + 1);
+                if (num < kk) atomicMax(&slots[num], static_cast<uint32_t>(idx));
+            }
+            __syncwarp();
+            for (uint32_t j = lane; j < kk; j += 32) out[o + j] = indices[start + slots[j]];
+            __syncwarp();
+        } else {
+            unsigned long long *gs = reinterpret_cast<unsigned long long *>(out + o);
+            for (int64_t j = lane; j < k; j += 32) gs[j] = static_cast<unsigned long long>(j);
+            __syncwarp();
+            for (int64_t idx = k + lane; idx < deg; idx += 32) {
+                const uint32_t num = xorwow_next(rng) % static_cast<uint32_t>(idx + 1);
+                if (static_cast<int64_t>(num) < k) atomicMax(&gs[num], static_cast<unsigned long long>(idx));
+            }
+            __syncwarp();
+            for (int64_t j = lane; j < k; j += 32) {
+                const int64_t pos = static_cast<int64_t>(gs[j]);
+                out[o + j] = indices[start + pos];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Ordered hash table (first occurrence wins).  Slot = {key, first index, local id}, 16 bytes.
+// Capacity is a power of two >= 2*(S+E), derived ON THE DEVICE from the hop's sizes so the fused k-hop path clears
+// and probes only what the hop needs.
+// ------------------------------------------------------------------------------------------------------------------
+struct __align__(16) Slot {
+    long long key;
+    unsigned int index;
+    unsigned int local;
+};
+constexpr long long kEmptyKey = -1;
+
+__device__ __forceinline__ int table_log2(int64_t n_items, int max_log2)
+{
+    int lg = 10;
+    if (n_items > 512) lg = 64 - __clzll(static_cast<unsigned long long>(2 * n_items - 1));
+    return lg > max_log2 ? max_log2 : lg;
+}
+__device__ __forceinline__ uint64_t table_hash(long long key, int lg)
+{
+    return (static_cast<uint64_t>(key) * 0x9E3779B97F4A7C15ull) >> (64 - lg);
+}
+
+__global__ void __launch_bounds__(256)
+    table_clear_kernel(Slot *__restrict__ table, int max_log2, int64_t S_arg, const int64_t *__restrict__ d_S,
+                       int64_t E_arg, const int64_t *__restrict__ d_E)
+{
+    const int64_t n = dev_size(S_arg, d_S) + dev_size(E_arg, d_E);
+    const uint64_t cap = 1ull << table_log2(n, max_log2);
+    int4 *t = reinterpret_cast<int4 *>(table);
+    const int4 empty = make_int4(-1, -1, -1, -1);
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < cap;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        t[i] = empty;
+}
+
+// Kernel C: insert concat(seeds, outputs); remember each item's slot.
+__global__ void __launch_bounds__(256)
+    hash_insert_kernel(const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S,
+                       const int64_t *__restrict__ outputs, int64_t E_arg, const int64_t *__restrict__ d_E,
+                       Slot *__restrict__ table, int max_log2, uint32_t *__restrict__ pos)
+{
+    const int64_t S = dev_size(S_arg, d_S), E = dev_size(E_arg, d_E);
+    const int64_t n = S + E;
+    const int lg = table_log2(n, max_log2);
+    const uint64_t mask = (1ull << lg) - 1;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const long long key = i < S ? seeds[i] : outputs[i - S];
+        uint64_t p = table_hash(key, lg);
+        while (true) {
+            const unsigned long long prev =
+                atomicCAS(reinterpret_cast<unsigned long long *>(&table[p].key),
+                          static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+            if (prev == static_cast<unsigned long long>(kEmptyKey) || prev == static_cast<unsigned long long>(key)) {
+                atomicMin(&table[p].index, static_cast<unsigned int>(i));
+                break;
+            }
+            p = (p + 1) & mask;
+        }
+        pos[i] = static_cast<uint32_t>(p);
+    }
+}
+
+// Kernel D: first-occurrence flags -> chained scan -> frontier + local ids.   (quiver_sample.cu:39-61)
+__global__ void __launch_bounds__(kScanThreads)
+    frontier_scan_kernel(int64_t S_arg, const int64_t *__restrict__ d_S, int64_t E_arg, const int64_t *__restrict__ d_E,
+                         Slot *__restrict__ table, const uint32_t *__restrict__ pos, int64_t *__restrict__ frontier,
+                         int64_t *__restrict__ d_F, ScanState st, int n_tiles)
+{
+    const int64_t n = dev_size(S_arg, d_S) + dev_size(E_arg, d_E);
+    const int tile = take_ticket(st);
+    const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
+    long long key[kScanItems];
+    uint32_t p[kScanItems];
+    bool first[kScanItems];
+    long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        first[j] = false;
+        key[j] = 0;
+        p[j] = 0;
+        if (i < n) {
+            p[j] = pos[i];
+            const int4 s = *reinterpret_cast<const int4 *>(&table[p[j]]);
+            key[j] = (static_cast<long long>(static_cast<unsigned int>(s.y)) << 32) | static_cast<unsigned int>(s.x);
+            first[j] = static_cast<unsigned int>(s.z) == static_cast<unsigned int>(i);
+        }
+        sum += first[j] ? 1 : 0;
+    }
+    long long excl = chained_scan(sum, st, tile, n_tiles, d_F);
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        if (first[j]) {
+            frontier[excl] = key[j];
+            table[p[j]].local = static_cast<unsigned int>(excl);
+            excl++;
+        }
+    }
+}
+
+// Kernel E: col_idx[e] = local id of outputs[e]; optionally row_idx[e] by binary search over out_ptr
+// (quiver_sample.cu:244-251 and :341-351).
+__global__ void __launch_bounds__(256)
+    emit_edges_kernel(int64_t S_arg, const int64_t *__restrict__ d_S, int64_t E_arg, const int64_t *__restrict__ d_E,
+                      const Slot *__restrict__ table, const uint32_t *__restrict__ pos, int64_t *__restrict__ col_idx,
+                      int64_t *__restrict__ row_idx, const int64_t *__restrict__ out_ptr)
+{
+    const int64_t S = dev_size(S_arg, d_S), E = dev_size(E_arg, d_E);
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        col_idx[e] = table[pos[S + e]].local;
+        if (row_idx) {
+            // largest i with out_ptr[i] <= e  (seeds with zero count share an offset with their successor)
+            int64_t lo = 0, hi = S;
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (out_ptr[mid] <= e)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            row_idx[e] = lo;
+        }
+    }
+}
+
+__global__ void set_meta_kernel(int64_t *meta, int idx, int64_t value) { meta[idx] = value; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// cal_next (cuda_random.cu.hpp:71-104): one thread per node, neighbours visited in CSR order so the fp32 product is
+// formed in the reference's order (bit-identical results).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+    cal_next_kernel(const float *__restrict__ last_prob, float *__restrict__ cur_prob, int64_t N, int k,
+                    const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices)
+{
+    for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row < N;
+         row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t start = indptr[row];
+        const int64_t deg = indptr[row + 1] - start;
+        if (deg == 0) {
+            cur_prob[row] = 0;
+            continue;
+        }
+        float acc = 1.0f;
+        for (int64_t i = start; i < start + deg; i++) {
+            const int64_t u = indices[i];
+            const int64_t udeg = indptr[u + 1] - indptr[u];
+            float skip;
+            if (udeg == 0)
+                skip = 1;
+            else if (udeg <= k)
+                skip = 1 - last_prob[u];
+            else
+                skip = 1 - last_prob[u] + last_prob[u] * (udeg - k) / udeg;
+            acc *= skip;
+        }
+        cur_prob[row] = 1 - (1 - last_prob[row]) * acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------------------------
+struct Buffer {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return QV_OK;
+        size_t want = cap ? cap : 4096;
+        while (want < bytes) want *= 2;
+        if (ptr) {
+            QV_CUDA(cudaFree(ptr));
+            ptr = nullptr;
+            cap = 0;
+        }
+        QV_CUDA(cudaMalloc(&ptr, want));
+        cap = want;
+        return QV_OK;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+inline int tiles_for(int64_t n) { return static_cast<int>(std::max<int64_t>(1, (n + kScanTile - 1) / kScanTile)); }
+inline int host_log2_cap(int64_t n_items)
+{
+    int lg = 10;
+    if (n_items > 512) lg = 64 - __builtin_clzll(static_cast<unsigned long long>(2 * n_items - 1));
+    return lg;
+}
+}  // namespace
+}  // namespace qv
+
+using namespace qv;
+
+struct qv_sampler {
+    int device = 0;
+    const int64_t *indptr = nullptr;
+    const int64_t *indices = nullptr;
+    int64_t n_nodes = 0, n_edges = 0;
+    int n_sm = 148;
+
+    int64_t *d_meta = nullptr;  // kMetaWords device scalars
+    int64_t *h_meta = nullptr;  // pinned mirror
+    Buffer scan;                // two scan-state regions
+    size_t scan_region_words = 0;
+    Buffer table;  // Slot[2^table_log2]
+    int table_log2 = 0;
+    Buffer pos;      // uint32[n items]
+    Buffer out_ptr;  // int64[S]      (fused path / reindex_single)
+    Buffer nbr;      // int64[E]      (fused path: sampled neighbour ids)
+    Buffer rng_mats;   // XORWOW skip matrices (device copy)
+    Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
+    int64_t rng_cache_blocks = 0;
+    Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+};
+
+namespace
+{
+int ensure_scan(qv_sampler *s, int64_t max_items)
+{
+    const size_t words = static_cast<size_t>(tiles_for(max_items)) + 2;
+    const size_t region = (words + 15) & ~size_t(15);
+    if (region > s->scan_region_words) {
+        QV_TRY(s->scan.ensure(region * 2 * sizeof(unsigned long long)));
+        s->scan_region_words = s->scan.cap / (2 * sizeof(unsigned long long));
+    }
+    return QV_OK;
+}
+ScanState scan_region(qv_sampler *s, int which)
+{
+    return ScanState{static_cast<unsigned long long *>(s->scan.ptr) + which * s->scan_region_words};
+}
+int zero_scan_regions(qv_sampler *s, int64_t items0, int64_t items1, cudaStream_t st)
+{
+    // only the descriptors that will be used need zeroing
+    const size_t w0 = static_cast<size_t>(tiles_for(items0)) + 2, w1 = static_cast<size_t>(tiles_for(items1)) + 2;
+    QV_CUDA(cudaMemsetAsync(scan_region(s, 0).words, 0, w0 * 8, st));
+    if (items1 >= 0) QV_CUDA(cudaMemsetAsync(scan_region(s, 1).words, 0, w1 * 8, st));
+    return QV_OK;
+}
+int ensure_table(qv_sampler *s, int64_t max_items)
+{
+    const int lg = host_log2_cap(max_items);
+    if (lg > s->table_log2) {
+        QV_REQUIRE(lg <= 33, "reindex: %lld items exceed the hash table limit", (long long)max_items);
+        QV_TRY(s->table.ensure((size_t(1) << lg) * sizeof(Slot)));
+        s->table_log2 = lg;
+    }
+    QV_TRY(s->pos.ensure(static_cast<size_t>(std::max<int64_t>(max_items, 1)) * sizeof(uint32_t)));
+    return QV_OK;
+}
+
+// XORWOW states for a launch over (up to) `rows_bound` seeds.  rand_seed == 0 (the reference's literal) is served
+// from a cache that only ever grows; other seeds are generated per launch.
+int rng_states_for(qv_sampler *s, uint64_t rand_seed, int64_t rows_arg, const int64_t *d_rows, int64_t rows_bound,
+                   cudaStream_t st, const uint32_t **states)
+{
+    const int64_t blocks = (rows_bound + kSampleTile - 1) / kSampleTile;
+    const size_t bytes_per_block = size_t(kRngStateWords) * kRngBlockThreads * sizeof(uint32_t);
+    if (!s->rng_mats.ptr) {
+        const size_t bytes = size_t(kXorwowBits) * kXorwowWords * kRngBlockThreads * sizeof(uint32_t);
+        QV_TRY(s->rng_mats.ensure(bytes));
+        QV_CUDA(cudaMemcpy(s->rng_mats.ptr, xorwow_subseq_matrices_host(), bytes, cudaMemcpyHostToDevice));
+    }
+    if (rand_seed == 0) {
+        if (blocks > s->rng_cache_blocks) {
+            int64_t want = std::max<int64_t>(blocks, 1024);
+            want = std::max(want, s->rng_cache_blocks * 2);
+            // growing re-allocates: make sure nothing in flight still reads the old cache
+            QV_CUDA(cudaStreamSynchronize(st));
+            QV_TRY(s->rng_cache.ensure(static_cast<size_t>(want) * bytes_per_block));
+            QV_TRY(xorwow_fill_states(static_cast<const uint32_t *>(s->rng_mats.ptr), 0, want * kSampleTile, nullptr,
+                                      want, static_cast<uint32_t *>(s->rng_cache.ptr), st));
+            s->rng_cache_blocks = want;
+        }
+        *states = static_cast<const uint32_t *>(s->rng_cache.ptr);
+        return QV_OK;
+    }
+    if (static_cast<size_t>(blocks) * bytes_per_block > s->rng_tmp.cap) QV_CUDA(cudaStreamSynchronize(st));
+    QV_TRY(s->rng_tmp.ensure(static_cast<size_t>(std::max<int64_t>(blocks, 1)) * bytes_per_block));
+    QV_TRY(xorwow_fill_states(static_cast<const uint32_t *>(s->rng_mats.ptr), rand_seed, rows_arg, d_rows, blocks,
+                              static_cast<uint32_t *>(s->rng_tmp.ptr), st));
+    *states = static_cast<const uint32_t *>(s->rng_tmp.ptr);
+    return QV_OK;
+}
+
+int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
+                      int64_t k, int64_t *counts, int64_t *out_ptr, int64_t *d_total, int region, cudaStream_t st)
+{
+    const int n_tiles = tiles_for(S_bound);
+    count_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(s->indptr, s->n_nodes, seeds, S_arg, d_S, k, counts, out_ptr,
+                                                         d_total, scan_region(s, region), n_tiles);
+    QV_CHECK_LAUNCH("count_scan_kernel");
+    return QV_OK;
+}
+
+int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound, int64_t k,
+                  uint64_t rand_seed, const int64_t *out_ptr, int64_t *out, int64_t *row_out, const int64_t *d_row_off,
+                  cudaStream_t st)
+{
+    if (S_bound <= 0) return QV_OK;
+    const uint32_t *states = nullptr;
+    QV_TRY(rng_states_for(s, rand_seed, S_arg, d_S, S_bound, st, &states));
+    const int64_t blocks = (S_bound + kSampleTile - 1) / kSampleTile;
+    QV_REQUIRE(blocks < (int64_t(1) << 31), "sample: too many seeds (%lld)", (long long)S_bound);
+    if (k < 0 || k <= kSmemSlots) {
+        sample_rows_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, out, row_out, d_row_off);
+    } else {
+        sample_rows_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, out, row_out, d_row_off);
+    }
+    QV_CHECK_LAUNCH("sample_rows_kernel");
+    return QV_OK;
+}
+
+inline unsigned grid_for(int64_t items, int threads, int n_sm, int waves = 8)
+{
+    const int64_t blocks = (items + threads - 1) / threads;
+    return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(n_sm) * waves)));
+}
+
+// clear + insert + frontier scan + emit, sizes from device scalars (or host args when the pointers are null)
+int launch_reindex(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
+                   const int64_t *outputs, int64_t E_arg, const int64_t *d_E, int64_t E_bound, int64_t *frontier,
+                   int64_t *d_F, int64_t *col_idx, int64_t *row_idx, const int64_t *out_ptr, int scan_which,
+                   cudaStream_t st)
+{
+    const int64_t n_bound = S_bound + E_bound;
+    Slot *table = static_cast<Slot *>(s->table.ptr);
+    uint32_t *pos = static_cast<uint32_t *>(s->pos.ptr);
+    const uint64_t cap_bound = 1ull << host_log2_cap(n_bound);
+    table_clear_kernel<<<grid_for(static_cast<int64_t>(cap_bound), 256, s->n_sm), 256, 0, st>>>(
+        table, s->table_log2, S_arg, d_S, E_arg, d_E);
+    QV_CHECK_LAUNCH("table_clear_kernel");
+    if (n_bound > 0) {
+        hash_insert_kernel<<<grid_for(n_bound, 256, s->n_sm), 256, 0, st>>>(seeds, S_arg, d_S, outputs, E_arg, d_E,
+                                                                              table, s->table_log2, pos);
+        QV_CHECK_LAUNCH("hash_insert_kernel");
+    }
+    const int n_tiles = tiles_for(n_bound);
+    frontier_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(S_arg, d_S, E_arg, d_E, table, pos, frontier, d_F,
+                                                            scan_region(s, scan_which), n_tiles);
+    QV_CHECK_LAUNCH("frontier_scan_kernel");
+    if (E_bound > 0) {
+        emit_edges_kernel<<<grid_for(E_bound, 256, s->n_sm), 256, 0, st>>>(S_arg, d_S, E_arg, d_E, table, pos, col_idx,
+                                                                            row_idx, out_ptr);
+        QV_CHECK_LAUNCH("emit_edges_kernel");
+    }
+    return QV_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const int64_t *indices, int64_t n_edges,
+                      qv_sampler **out)
+{
+    QV_REQUIRE(out != nullptr, "qv_sampler_create: out is NULL");
+    *out = nullptr;
+    QV_REQUIRE(indptr != nullptr && n_nodes >= 0 && n_edges >= 0, "qv_sampler_create: bad CSR arguments");
+    QV_REQUIRE(indices != nullptr || n_edges == 0, "qv_sampler_create: indices is NULL");
+    DeviceGuard g(device);
+    qv_sampler *s = new (std::nothrow) qv_sampler();
+    QV_REQUIRE(s != nullptr, "qv_sampler_create: out of host memory");
+    s->device = device;
+    s->indptr = indptr;
+    s->indices = indices;
+    s->n_nodes = n_nodes;
+    s->n_edges = n_edges;
+    s->n_sm = sm_count(device);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&s->d_meta), kMetaWords * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemset(s->d_meta, 0, kMetaWords * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_meta), kMetaWords * sizeof(int64_t), 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (s->d_meta) cudaFree(s->d_meta);
+        delete s;
+        return fail(QV_ERR_CUDA, "qv_sampler_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return QV_OK;
+}
+
+int qv_sampler_destroy(qv_sampler *s)
+{
+    if (!s) return QV_OK;
+    DeviceGuard g(s->device);
+    cudaDeviceSynchronize();
+    s->scan.release();
+    s->table.release();
+    s->pos.release();
+    s->out_ptr.release();
+    s->nbr.release();
+    s->rng_mats.release();
+    s->rng_cache.release();
+    s->rng_tmp.release();
+    if (s->d_meta) cudaFree(s->d_meta);
+    if (s->h_meta) cudaFreeHost(s->h_meta);
+    delete s;
+    return QV_OK;
+}
+
+int qv_sample_count(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, int64_t *counts, int64_t *out_ptr,
+                    int64_t *total, qv_stream_t stream)
+{
+    QV_REQUIRE(s && total, "qv_sample_count: NULL argument");
+    QV_REQUIRE(S >= 0, "qv_sample_count: negative seed count");
+    *total = 0;
+    if (S == 0) return QV_OK;  // the reference launches a 0-block grid here (quiver.cu.hpp:388)
+    QV_REQUIRE(seeds && counts && out_ptr, "qv_sample_count: NULL array");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QV_TRY(ensure_scan(s, S));
+    QV_TRY(zero_scan_regions(s, S, -1, st));
+    QV_TRY(launch_count_scan(s, seeds, S, nullptr, S, k, counts, out_ptr, s->d_meta + kMetaE, 0, st));
+    QV_CUDA(cudaMemcpyAsync(s->h_meta + kMetaE, s->d_meta + kMetaE, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    QV_CUDA(cudaStreamSynchronize(st));
+    *total = s->h_meta[kMetaE];
+    return QV_OK;
+}
+
+int qv_sample_fill(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, uint64_t rand_seed,
+                   const int64_t *out_ptr, int64_t *neighbors, qv_stream_t stream)
+{
+    QV_REQUIRE(s, "qv_sample_fill: NULL sampler");
+    if (S <= 0) return QV_OK;
+    QV_REQUIRE(seeds && out_ptr, "qv_sample_fill: NULL array");
+    QV_REQUIRE(k < (int64_t(1) << 31), "qv_sample_fill: fan-out %lld too large", (long long)k);
+    DeviceGuard g(s->device);
+    return launch_sample(s, seeds, S, nullptr, S, k, rand_seed, out_ptr, neighbors, nullptr, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int qv_reindex(qv_sampler *s, const int64_t *inputs, int64_t S, const int64_t *outputs, int64_t tot,
+               const int64_t *counts, int64_t *frontier, int64_t *row_idx, int64_t *col_idx, int64_t *n_frontier,
+               qv_stream_t stream)
+{
+    QV_REQUIRE(s && n_frontier, "qv_reindex: NULL argument");
+    QV_REQUIRE(S >= 0 && tot >= 0, "qv_reindex: negative size");
+    *n_frontier = 0;
+    if (S + tot == 0) return QV_OK;
+    QV_REQUIRE(S + tot < (int64_t(1) << 32) - 1, "qv_reindex: %lld items exceed 2^32", (long long)(S + tot));
+    QV_REQUIRE(frontier && (inputs || S == 0) && (outputs || tot == 0), "qv_reindex: NULL array");
+    QV_REQUIRE((row_idx && col_idx && counts) || tot == 0, "qv_reindex: NULL edge arrays");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    QV_TRY(ensure_scan(s, S + tot));
+    QV_TRY(ensure_table(s, S + tot));
+    QV_TRY(s->out_ptr.ensure(static_cast<size_t>(std::max<int64_t>(S, 1)) * sizeof(int64_t)));
+    QV_TRY(zero_scan_regions(s, S, S + tot, st));
+    int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
+    if (S > 0 && tot > 0) {
+        const int n_tiles = tiles_for(S);
+        plain_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(counts, S, optr, nullptr, scan_region(s, 0), n_tiles);
+        QV_CHECK_LAUNCH("plain_scan_kernel");
+    }
+    QV_TRY(launch_reindex(s, inputs, S, nullptr, S, outputs, tot, nullptr, tot, frontier, s->d_meta + kMetaF, col_idx,
+                          row_idx, optr, 1, st));
+    QV_CUDA(cudaMemcpyAsync(s->h_meta + kMetaF, s->d_meta + kMetaF, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    QV_CUDA(cudaStreamSynchronize(st));
+    *n_frontier = s->h_meta[kMetaF];
+    return QV_OK;
+}
+
+int qv_khop_bounds(int64_t S, const int64_t *sizes, int n_hops, int64_t *bound_nodes, int64_t *bound_edges)
+{
+    QV_REQUIRE(sizes && bound_nodes && bound_edges, "qv_khop_bounds: NULL argument");
+    QV_REQUIRE(n_hops >= 1 && n_hops <= QV_MAX_HOPS, "qv_khop_bounds: n_hops must be in [1, %d]", QV_MAX_HOPS);
+    QV_REQUIRE(S >= 0, "qv_khop_bounds: negative seed count");
+    bound_nodes[0] = S;
+    for (int h = 0; h < n_hops; h++) {
+        if (sizes[h] < 0)
+            return fail(QV_ERR_UNSUPPORTED, "qv_khop: sizes[%d] = %lld has no static bound; use the per-hop calls", h,
+                        (long long)sizes[h]);
+        const __int128 e = static_cast<__int128>(bound_nodes[h]) * sizes[h];
+        if (e + bound_nodes[h] >= (static_cast<__int128>(1) << 32) - 1)
+            return fail(QV_ERR_UNSUPPORTED, "qv_khop: hop %d bound exceeds 2^32 items; use the per-hop calls", h);
+        bound_edges[h] = static_cast<int64_t>(e);
+        bound_nodes[h + 1] = bound_nodes[h] + bound_edges[h];
+    }
+    return QV_OK;
+}
+
+int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+            int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream)
+{
+    QV_REQUIRE(s && sizes && out_nodes && out_edges, "qv_khop: NULL argument");
+    int64_t bn[QV_MAX_HOPS + 1], be[QV_MAX_HOPS];
+    QV_TRY(qv_khop_bounds(S, sizes, n_hops, bn, be));
+    for (int h = 0; h <= n_hops; h++) out_nodes[h] = h == 0 ? S : 0;
+    for (int h = 0; h < n_hops; h++) out_edges[h] = 0;
+    if (S == 0) return QV_OK;
+    QV_REQUIRE(seeds && n_id && edge_buf, "qv_khop: NULL array");
+    DeviceGuard g(s->device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    int64_t max_nodes = 0, max_edges = 0;
+    for (int h = 0; h < n_hops; h++) {
+        max_nodes = std::max(max_nodes, bn[h]);
+        max_edges = std::max(max_edges, be[h]);
+    }
+    QV_TRY(ensure_scan(s, bn[n_hops]));
+    QV_TRY(ensure_table(s, bn[n_hops]));
+    QV_TRY(s->out_ptr.ensure(static_cast<size_t>(max_nodes) * sizeof(int64_t)));
+    QV_TRY(s->nbr.ensure(static_cast<size_t>(std::max<int64_t>(max_edges, 1)) * sizeof(int64_t)));
+    int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
+    int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
+
+    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaS, S);
+    QV_CHECK_LAUNCH("set_meta_kernel");
+    for (int h = 0; h < n_hops; h++) {
+        QV_REQUIRE(edge_buf[h] != nullptr || be[h] == 0, "qv_khop: edge_buf[%d] is NULL", h);
+        int64_t *m = s->d_meta + kMetaStride * h;
+        const int64_t *d_S = m + kMetaS;
+        int64_t *d_E = m + kMetaE;
+        int64_t *d_F = m + kMetaF;
+        const int64_t *hop_seeds = h == 0 ? seeds : n_id;
+        QV_TRY(zero_scan_regions(s, bn[h], bn[h] + be[h], st));
+        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st));
+        // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
+        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st));
+        QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr, nullptr,
+                              1, st));
+        // the next hop's seed count is this hop's frontier size
+        QV_CUDA(cudaMemcpyAsync(m + kMetaStride + kMetaS, d_F, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    QV_CUDA(cudaStreamSynchronize(st));
+    for (int h = 0; h < n_hops; h++) {
+        out_edges[h] = s->h_meta[kMetaStride * h + kMetaE];
+        out_nodes[h + 1] = s->h_meta[kMetaStride * h + kMetaF];
+    }
+    return QV_OK;
+}
+
+int qv_cal_neighbor_prob(qv_sampler *s, const float *last_prob, float *cur_prob, int64_t n, int k, qv_stream_t stream)
+{
+    QV_REQUIRE(s && last_prob && cur_prob, "qv_cal_neighbor_prob: NULL argument");
+    QV_REQUIRE(n >= 0 && n <= s->n_nodes, "qv_cal_neighbor_prob: n = %lld outside [0, %lld]", (long long)n,
+               (long long)s->n_nodes);
+    if (n == 0) return QV_OK;
+    DeviceGuard g(s->device);
+    cal_next_kernel<<<grid_for(n, 128, s->n_sm, 16), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        last_prob, cur_prob, n, k, s->indptr, s->indices);
+    QV_CHECK_LAUNCH("cal_next_kernel");
+    return QV_OK;
+}
+
+}  // extern "C"

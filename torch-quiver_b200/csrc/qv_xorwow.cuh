@@ -1,0 +1,65 @@
+// qv_xorwow.cuh -- XORWOW generator state compatible with cuRAND's device API stream, without cuRAND.
+//
+// The reference sampler draws from curand_init(seed = rand_seed*gridDim.x + blockIdx.x, subsequence = thread id in
+// the 128-thread block, offset 0) EVERY launch (include/quiver/cuda_random.cu.hpp:21-23); the sub-sequence
+// skip-ahead (2^67 steps per sub-sequence) costs each thread a chain of 160x160 GF(2) matrix products and dominates
+// small launches.  Here the 128 skip-ahead maps P_q = (step^(2^67))^q are built once on the host (qv_xorwow.cu),
+// kept in device memory in a lane-coalesced layout, and applied by one kernel that fills a cache of ready-to-use
+// generator states [block][6 words][128 threads].  Sampling kernels then start from a 24-byte load.
+//
+// Arithmetic follows the published XORWOW recurrence (Marsaglia) with cuRAND's Weyl constant and seeding:
+// CUDA 12.9 curand_kernel.h:800-825 (seeding), :863-874 (step), :316-334 / :720-737 (skip-ahead semantics).
+#pragma once
+#include <cstdint>
+
+namespace qv
+{
+constexpr int kXorwowWords = 5;
+constexpr int kXorwowBits = 160;
+constexpr int kRngBlockThreads = 128;  // the reference's block(32,4): quiver.cu.hpp:384-387
+constexpr int kRngStateWords = 6;      // d, v[0..4]
+
+struct Xorwow {
+    uint32_t d, v0, v1, v2, v3, v4;
+};
+
+__host__ __device__ __forceinline__ uint32_t xorwow_next(Xorwow &s)
+{
+    const uint32_t t = s.v0 ^ (s.v0 >> 2);
+    s.v0 = s.v1;
+    s.v1 = s.v2;
+    s.v2 = s.v3;
+    s.v3 = s.v4;
+    s.v4 = (s.v4 ^ (s.v4 << 4)) ^ (t ^ (t << 1));
+    s.d += 362437u;
+    return s.v4 + s.d;
+}
+
+// State of curand_init(seed, 0, 0): the seed scrambling only.
+__host__ __device__ __forceinline__ Xorwow xorwow_seed(uint64_t seed)
+{
+    const uint32_t s0 = static_cast<uint32_t>(seed) ^ 0xaad26b49u;
+    const uint32_t s1 = static_cast<uint32_t>(seed >> 32) ^ 0xf7dcefddu;
+    const uint32_t t0 = 1099087573u * s0;
+    const uint32_t t1 = 2591861531u * s1;
+    Xorwow s;
+    s.d = 6615241u + t1 + t0;
+    s.v0 = 123456789u + t0;
+    s.v1 = 362436069u ^ t0;
+    s.v2 = 521288629u + t1;
+    s.v3 = 88675123u ^ t1;
+    s.v4 = 5783321u + t0;
+    return s;
+}
+
+// Host: the 128 sub-sequence skip matrices in device layout [bit r (160)][word (5)][q (128)] (uint32).
+// Returns a pointer to a process-lifetime host array of 160*5*128 words.
+const uint32_t *xorwow_subseq_matrices_host();
+
+// Fill generator states for the reference launch geometry of `rows` seeds (rows = d_rows ? *d_rows : rows_arg):
+// grid = ceil(rows/64); block b < grid, thread q gets curand_init(rand_seed*grid + b, q, 0).
+// Layout: states[((b * 6) + word) * 128 + q].  `n_blocks` = blocks to launch (>= grid; the rest exit).
+int xorwow_fill_states(const uint32_t *matrices_dev, uint64_t rand_seed, int64_t rows_arg, const int64_t *d_rows,
+                       int64_t n_blocks, uint32_t *states_dev, cudaStream_t stream);
+
+}  // namespace qv

@@ -1,0 +1,236 @@
+"""quiver.Feature -- tiered feature store: hot rows in HBM (replicated per GPU or striped over the NVLink clique), cold
+rows in pinned host memory, one gather kernel over all tiers.  Reference: srcs/python/quiver/feature.py:17-458.
+
+Placement arithmetic, kwargs and pickling behaviour follow the reference (SURVEY.md 8(b') items 5-8).  Differences:
+the `feature_order[idx]` indirection runs inside the gather kernel instead of as a separate torch index op
+(feature.py:300-301), and `from_cpu_tensor` returns self (the reference returns None) so the README's chained form
+works.  The disk-mmap tier (feature.py:84-93, 309-333) and DistFeature / PartitionInfo are out of scope.
+"""
+from typing import List
+
+import torch
+
+from .shard_tensor import ShardTensor, ShardTensorConfig
+from .utils import CSRTopo, Topo, parse_size, reindex_feature
+
+__all__ = ["Feature", "DeviceConfig"]
+
+
+class DeviceConfig:
+    """Pre-partitioned placement: one tensor (or .pt path) per GPU plus the host part (feature.py:11-14)."""
+
+    def __init__(self, gpu_parts, cpu_part):
+        self.gpu_parts = gpu_parts
+        self.cpu_part = cpu_part
+
+
+def _load_part(part):
+    return torch.load(part) if isinstance(part, str) else part
+
+
+class Feature(object):
+    """
+    >>> feature = Feature(0, device_list=[0, 1], device_cache_size='200M')
+    >>> feature.from_cpu_tensor(cpu_tensor)
+    >>> rows = feature[node_idx]            # [len(node_idx), D] on cuda:rank
+
+    Args:
+        rank (int): device the gather kernel runs on
+        device_list ([int]): devices that hold cached rows
+        device_cache_size (int | str): cache budget per device, e.g. "0.9M", "3GB"
+        cache_policy (str): "device_replicate" (every GPU caches the same hot rows) or "p2p_clique_replicate"
+            (hot rows are striped over the GPUs of an NVLink clique and read peer-to-peer)
+        csr_topo (quiver.CSRTopo): if given, rows are re-ordered by degree so the cache holds the hottest rows
+    """
+
+    def __init__(self, rank: int, device_list: List[int], device_cache_size: int = 0,
+                 cache_policy: str = "device_replicate", csr_topo: CSRTopo = None):
+        assert cache_policy in ["device_replicate", "p2p_clique_replicate"], \
+            "Feature cache_policy should be one of [device_replicate, p2p_clique_replicate]"
+        self.device_cache_size = device_cache_size
+        self.cache_policy = cache_policy
+        self.device_list = device_list
+        self.device_tensor_list = {}
+        self.clique_tensor_list = {}
+        self.rank = rank
+        self.topo = Topo(self.device_list)
+        self.csr_topo = csr_topo
+        self.feature_order = None
+        self.cpu_part = None
+        self.ipc_handle_ = None
+        assert self.clique_device_symmetry_check(), f"\n{self.topo.info()}\nDifferent p2p clique size NOT equal"
+
+    # ---- placement ------------------------------------------------------------------------------------------------
+    def clique_device_symmetry_check(self):
+        if self.cache_policy == "device_replicate":
+            return True
+        second = self.topo.p2pClique2Device.get(1, [])
+        return len(second) == 0 or len(second) == len(self.topo.p2pClique2Device[0])
+
+    def cal_size(self, cpu_tensor: torch.Tensor, cache_memory_budget: int):
+        return cache_memory_budget // (cpu_tensor.shape[1] * cpu_tensor.element_size())
+
+    def partition(self, cpu_tensor: torch.Tensor, cache_memory_budget: int):
+        cache_size = self.cal_size(cpu_tensor, cache_memory_budget)
+        return [cpu_tensor[:cache_size], cpu_tensor[cache_size:]]
+
+    def _my_store(self):
+        if self.cache_policy == "device_replicate":
+            return self.device_tensor_list[self.rank]
+        return self.clique_tensor_list[self.topo.get_clique_id(self.rank)]
+
+    def _attach_cpu_part(self):
+        if self.cpu_part is None or self.cpu_part.numel() == 0:
+            return
+        if self.cache_policy == "device_replicate":
+            store, key = self.device_tensor_list, self.rank
+        else:
+            store, key = self.clique_tensor_list, self.topo.get_clique_id(self.rank)
+        shard_tensor = store.get(key) or ShardTensor(self.rank, ShardTensorConfig({}))
+        shard_tensor.append(self.cpu_part, -1)
+        store[key] = shard_tensor
+
+    def from_cpu_tensor(self, cpu_tensor: torch.Tensor):
+        """Place a [N, D] CPU tensor across the tiers (reference: feature.py:194-281)."""
+        clique0 = self.topo.p2pClique2Device.get(0, [])
+        if self.cache_policy == "device_replicate":
+            cache_memory_budget = parse_size(self.device_cache_size)
+            shuffle_ratio = 0.0
+        else:
+            cache_memory_budget = parse_size(self.device_cache_size) * len(clique0)
+            shuffle_ratio = self.cal_size(cpu_tensor, cache_memory_budget) / cpu_tensor.size(0)
+
+        if self.csr_topo is not None:
+            if self.csr_topo.feature_order is None:
+                cpu_tensor, self.csr_topo.feature_order = reindex_feature(self.csr_topo, cpu_tensor, shuffle_ratio)
+            self.feature_order = self.csr_topo.feature_order.to(self.rank)
+
+        cache_part, self.cpu_part = self.partition(cpu_tensor, cache_memory_budget)
+        self.cpu_part = self.cpu_part.clone()
+        if cache_part.shape[0] > 0 and self.cache_policy == "device_replicate":
+            for device in self.device_list:
+                shard_tensor = ShardTensor(self.rank, ShardTensorConfig({}))
+                shard_tensor.append(cache_part, device)
+                self.device_tensor_list[device] = shard_tensor
+        elif cache_part.shape[0] > 0:
+            block_size = self.cal_size(cpu_tensor, cache_memory_budget // len(clique0))
+            for clique_id in (0, 1):
+                devices = self.topo.p2pClique2Device.get(clique_id, [])
+                if not devices:
+                    continue
+                shard_tensor = ShardTensor(self.rank, ShardTensorConfig({}))
+                cur = 0
+                for i, device in enumerate(devices):
+                    last = i == len(devices) - 1  # the last GPU of the clique takes the remainder
+                    shard_tensor.append(cache_part[cur:] if last else cache_part[cur:cur + block_size], device)
+                    cur += block_size
+                self.clique_tensor_list[clique_id] = shard_tensor
+        self._attach_cpu_part()
+        return self
+
+    def from_mmap(self, np_array, device_config: DeviceConfig):
+        """Place pre-partitioned parts (reference: feature.py:95-192).  `np_array` is an optional numpy (mmap) array
+        the parts index into; parts may also be tensors or paths to saved tensors."""
+        assert len(device_config.gpu_parts) == len(self.device_list)
+
+        def materialise(part):
+            part = _load_part(part)
+            if np_array is None:
+                return part.to(dtype=torch.float32)
+            return torch.from_numpy(np_array[part.numpy()]).to(dtype=torch.float32)
+
+        if self.cache_policy == "device_replicate":
+            for device in self.device_list:
+                shard_tensor = ShardTensor(self.rank, ShardTensorConfig({}))
+                shard_tensor.append(materialise(device_config.gpu_parts[device]), device)
+                self.device_tensor_list[device] = shard_tensor
+        else:
+            for clique_id in (0, 1):
+                devices = self.topo.p2pClique2Device.get(clique_id, [])
+                if not devices:
+                    continue
+                shard_tensor = ShardTensor(self.rank, ShardTensorConfig({}))
+                for device in devices:
+                    shard_tensor.append(materialise(device_config.gpu_parts[device]), device)
+                    self.device_tensor_list[device] = shard_tensor
+                self.clique_tensor_list[clique_id] = shard_tensor
+        self.cpu_part = materialise(device_config.cpu_part)
+        self._attach_cpu_part()
+        return self
+
+    def set_local_order(self, local_order):
+        """`local_order[i]` = original id of stored row i  =>  feature_order = its inverse (feature.py:283-294)."""
+        local_range = torch.arange(end=local_order.size(0), dtype=torch.int64, device=self.rank)
+        self.feature_order = torch.zeros_like(local_range)
+        self.feature_order[local_order.to(self.rank)] = local_range
+
+    # ---- the hot call ---------------------------------------------------------------------------------------------
+    def __getitem__(self, node_idx: torch.Tensor):
+        self.lazy_init_from_ipc_handle()
+        node_idx = node_idx.to(self.rank)
+        return self._my_store().gather(node_idx, self.feature_order)
+
+    def size(self, dim: int):
+        self.lazy_init_from_ipc_handle()
+        return self._my_store().size(dim)
+
+    def dim(self):
+        return len(self.shape)
+
+    @property
+    def shape(self):
+        self.lazy_init_from_ipc_handle()
+        return self._my_store().shape
+
+    # ---- mp.spawn plumbing (reference: feature.py:375-458) ---------------------------------------------------------
+    @property
+    def ipc_handle(self):
+        return self.ipc_handle_
+
+    @ipc_handle.setter
+    def ipc_handle(self, ipc_handle):
+        self.ipc_handle_ = ipc_handle
+
+    def share_ipc(self):
+        self.cpu_part.share_memory_()
+        stores = self.device_tensor_list if self.cache_policy == "device_replicate" else self.clique_tensor_list
+        gpu_ipc_handle_dict = {key: st.share_ipc()[0] for key, st in stores.items()}
+        cpu_part = self.cpu_part if self.cpu_part.numel() > 0 else None
+        return gpu_ipc_handle_dict, cpu_part, self.device_list, self.device_cache_size, self.cache_policy, self.csr_topo
+
+    def from_gpu_ipc_handle_dict(self, gpu_ipc_handle_dict, cpu_tensor):
+        if self.cache_policy == "device_replicate":
+            key, store = self.rank, self.device_tensor_list
+        else:
+            key, store = self.topo.get_clique_id(self.rank), self.clique_tensor_list
+        ipc_handle = gpu_ipc_handle_dict.get(key, []), cpu_tensor, ShardTensorConfig({})
+        store[key] = ShardTensor.new_from_share_ipc(ipc_handle, self.rank)
+        self.cpu_part = cpu_tensor
+
+    @classmethod
+    def new_from_ipc_handle(cls, rank, ipc_handle):
+        gpu_ipc_handle_dict, cpu_part, device_list, device_cache_size, cache_policy, csr_topo = ipc_handle
+        feature = cls(rank, device_list, device_cache_size, cache_policy)
+        feature.from_gpu_ipc_handle_dict(gpu_ipc_handle_dict, cpu_part)
+        if csr_topo is not None:
+            feature.feature_order = csr_topo.feature_order.to(rank)
+        feature.csr_topo = csr_topo
+        return feature
+
+    @classmethod
+    def lazy_from_ipc_handle(cls, ipc_handle):
+        _, _, device_list, device_cache_size, cache_policy, _ = ipc_handle
+        feature = cls(device_list[0], device_list, device_cache_size, cache_policy)
+        feature.ipc_handle = ipc_handle
+        return feature
+
+    def lazy_init_from_ipc_handle(self):
+        if self.ipc_handle is None:
+            return
+        self.rank = torch.cuda.current_device()
+        gpu_ipc_handle_dict, cpu_part, _, _, _, csr_topo = self.ipc_handle
+        self.from_gpu_ipc_handle_dict(gpu_ipc_handle_dict, cpu_part)
+        self.csr_topo = csr_topo
+        if csr_topo is not None and csr_topo.feature_order is not None:
+            self.feature_order = csr_topo.feature_order.to(self.rank)
+        self.ipc_handle = None

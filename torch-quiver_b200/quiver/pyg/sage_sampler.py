@@ -1,0 +1,124 @@
+"""quiver.pyg.GraphSageSampler -- PyG NeighborSampler-compatible k-hop sampler on one B200.
+Reference: srcs/python/quiver/pyg/sage_sampler.py:40-178 (MixedGraphSageSampler / SampleJob are out of scope)."""
+from dataclasses import dataclass
+from typing import List, NamedTuple, Tuple
+
+import torch
+
+import torch_quiver as qv
+
+from .. import utils as quiver_utils
+
+__all__ = ["GraphSageSampler", "Adj"]
+
+
+class Adj(NamedTuple):
+    edge_index: torch.Tensor
+    e_id: torch.Tensor
+    size: Tuple[int, int]
+
+    def to(self, *args, **kwargs):
+        return Adj(self.edge_index.to(*args, **kwargs), self.e_id.to(*args, **kwargs), self.size)
+
+
+@dataclass(frozen=True)
+class _FakeDevice(object):
+    pass
+
+
+class GraphSageSampler:
+    r"""Behaves like PyG's `NeighborSampler`: `sample(seeds)` returns `(n_id, batch_size, adjs)` with `adjs` ordered
+    outermost hop first, `adj.edge_index[0]` indexing into `n_id` (sources) and `edge_index[1]` into the hop's targets.
+
+    Args:
+        csr_topo (quiver.CSRTopo): graph topology
+        sizes ([int]): neighbours to sample per hop; -1 = all neighbours
+        device (int): GPU the kernels run on
+        mode (str): "GPU" (topology in HBM) or "UVA" (indices stay in pinned host memory, read zero-copy).
+            "CPU" is accepted by the reference; this build has no CPU path and raises for it.
+    """
+
+    def __init__(self, csr_topo: quiver_utils.CSRTopo, sizes: List[int], device=0, mode="UVA"):
+        assert mode in ["UVA", "GPU", "CPU"], "sampler mode should be one of [UVA, GPU]"
+        assert device is _FakeDevice or mode == "CPU" or (device >= 0 and mode != "CPU"), \
+            "Device setting and Mode setting not compatitive"
+        if mode == "CPU":
+            raise NotImplementedError("mode='CPU' is not part of the B200 build (no CPU sampling path); "
+                                      "use mode='GPU' or 'UVA'")
+        self.sizes = list(sizes)
+        self.quiver = None
+        self.csr_topo = csr_topo
+        self.mode = mode
+        self.fused = True  # all hops in one C call; falls back per hop when a size is -1
+        if device is not _FakeDevice and device >= 0:
+            self.quiver = self._build(device)
+        self.device = device
+        self.ipc_handle_ = None
+
+    def _build(self, device):
+        edge_id = torch.zeros(1, dtype=torch.long)
+        return qv.device_quiver_from_csr_array(self.csr_topo.indptr, self.csr_topo.indices, edge_id, device,
+                                               self.mode != "UVA")
+
+    def lazy_init_quiver(self):
+        """A sampler unpickled in a spawned worker binds to that worker's current device (sage_sampler.py:98-113)."""
+        if self.quiver is not None:
+            return
+        self.device = torch.cuda.current_device()
+        self.quiver = self._build(self.device)
+
+    def sample_layer(self, batch, size):
+        self.lazy_init_quiver()
+        if not isinstance(batch, torch.Tensor):
+            batch = torch.tensor(batch)
+        n_id = batch.to(self.device)
+        size = size if size != -1 else self.csr_topo.node_count
+        return self.quiver.sample_neighbor(0, n_id, size)
+
+    def reindex(self, inputs, outputs, counts):
+        return self.quiver.reindex_single(inputs, outputs, counts)
+
+    def sample(self, input_nodes):
+        """k-hop sample.  Returns (n_id, batch_size, adjs) -- n_id FIRST, as the reference does
+        (sage_sampler.py:147; PyG's own loader yields (batch_size, n_id, adjs))."""
+        self.lazy_init_quiver()
+        if not isinstance(input_nodes, torch.Tensor):
+            input_nodes = torch.tensor(input_nodes)
+        nodes = input_nodes.to(self.device)
+        batch_size = len(nodes)
+        if self.fused and batch_size > 0 and all(s >= 0 for s in self.sizes):
+            try:
+                n_id, hops = self.quiver.sample_khop(nodes, self.sizes)
+            except qv.Unsupported:
+                pass
+            else:
+                adjs = [Adj(edge_index, torch.tensor([]), torch.LongTensor([n_src, n_dst]))
+                        for edge_index, n_src, n_dst in hops]
+                return n_id, batch_size, adjs[::-1]
+        adjs = []
+        for size in self.sizes:
+            out, cnt = self.sample_layer(nodes, size)
+            frontier, row_idx, col_idx = self.reindex(nodes, out, cnt)
+            edge_index = torch.stack([col_idx, row_idx], dim=0)  # [source local id, target (seed) position]
+            adjs.append(Adj(edge_index, torch.tensor([]), torch.LongTensor([frontier.size(0), nodes.size(0)])))
+            nodes = frontier
+        return nodes, batch_size, adjs[::-1]
+
+    def sample_prob(self, train_idx, total_node_count):
+        """Per-node access probability after len(sizes) hops from `train_idx` (sage_sampler.py:149-157)."""
+        self.lazy_init_quiver()
+        last_prob = torch.zeros(total_node_count, device=self.device)
+        last_prob[train_idx] = 1
+        for size in self.sizes:
+            cur_prob = torch.zeros(total_node_count, device=self.device)
+            self.quiver.cal_neighbor_prob(0, last_prob, cur_prob, size)
+            last_prob = cur_prob
+        return last_prob
+
+    def share_ipc(self):
+        return self.csr_topo, self.sizes, self.mode
+
+    @classmethod
+    def lazy_from_ipc_handle(cls, ipc_handle):
+        csr_topo, sizes, mode = ipc_handle
+        return cls(csr_topo, sizes, _FakeDevice, mode)

@@ -1,0 +1,145 @@
+"""Python-level ShardTensor: budgeted placement, cross-clique fallback, IPC plumbing.
+Reference: srcs/python/quiver/shard_tensor.py:51-213."""
+import torch
+
+import torch_quiver as torch_qv
+
+from .utils import Topo, parse_size
+
+
+class Offset:
+    def __init__(self, start, end):
+        self.start_, self.end_ = start, end
+
+    @property
+    def start(self):
+        return self.start_
+
+    @property
+    def end(self):
+        return self.end_
+
+
+class ShardTensorConfig:
+    """device -> memory budget ("200M", 3 * 2**30, ...), reference: shard_tensor.py:35-48."""
+
+    def __init__(self, device_memory_budget):
+        self.tensor_offset_device = {}
+        self.device_memory_budget = {d: parse_size(b) for d, b in device_memory_budget.items()}
+
+    @property
+    def device_list(self):
+        return list(self.device_memory_budget.keys())
+
+
+class ShardTensor:
+    def __init__(self, current_device: int, shard_tensor_config: ShardTensorConfig = None):
+        self.shard_tensor = torch_qv.ShardTensor(current_device)
+        self.current_device = current_device
+        self.shard_tensor_config = shard_tensor_config or ShardTensorConfig({})
+        self.topo = None
+        self.current_clique = None
+        self.cpu_tensor = None
+
+    def init_topo(self):
+        if self.current_clique is not None:
+            return
+        devices = set(self.shard_tensor_config.device_list)
+        devices.add(self.current_device)
+        self.topo = Topo(sorted(devices))
+        self.current_clique = self.topo.get_clique_id(self.current_device)
+
+    def append(self, cpu_tensor, device):
+        if device == -1:
+            if self.cpu_tensor is not None:
+                raise Exception("cpu tensor has been already appended")
+            self.cpu_tensor = cpu_tensor
+            self.shard_tensor.append(cpu_tensor, -1)
+            return
+        if self.shard_tensor_config.device_memory_budget.get(device) is not None:
+            raise Exception(f"{device} tensor has been already appended")
+        start = self.shard_tensor.size(0)
+        self.shard_tensor_config.tensor_offset_device[device] = Offset(start, start + cpu_tensor.shape[0])
+        self.shard_tensor_config.device_memory_budget[device] = cpu_tensor.numel() * cpu_tensor.element_size()
+        self.shard_tensor.append(cpu_tensor, device)
+
+    def partition(self, tensor, memory_budget):
+        return memory_budget // (tensor.shape[1] * tensor.element_size())
+
+    def from_cpu_tensor(self, tensor):
+        """Fill devices in config order up to their budgets, the rest goes to the pinned-host tier
+        (reference: shard_tensor.py:107-136)."""
+        cur = 0
+        for device_id, budget in self.shard_tensor_config.device_memory_budget.items():
+            if cur > tensor.shape[0]:
+                break
+            size = min(self.partition(tensor, budget), tensor.shape[0] - cur)
+            self.shard_tensor.append(tensor[cur:cur + size], device_id)
+            self.shard_tensor_config.tensor_offset_device[device_id] = Offset(cur, cur + size)
+            cur += size
+        if cur < tensor.shape[0]:
+            self.cpu_tensor = tensor[cur:]
+            self.shard_tensor.append(self.cpu_tensor, -1)
+
+    def collect_device(self, input_orders, nodes, inter_device, wait_results):
+        """Rows owned by a GPU outside this device's P2P clique: gather them ON that GPU, then copy
+        (reference: shard_tensor.py:138-152).  Never taken on NVSwitch machines (one clique)."""
+        off = self.shard_tensor_config.tensor_offset_device[inter_device]
+        mask = (nodes >= off.start) & (nodes < off.end)
+        request_nodes = torch.masked_select(nodes, mask).to(inter_device)
+        part_orders = torch.masked_select(input_orders, mask)
+        with torch.cuda.device(inter_device):
+            result = self.shard_tensor[request_nodes]
+        wait_results.append((part_orders, result.to(self.current_device)))
+
+    def __getitem__(self, nodes):
+        return self.gather(nodes)
+
+    def gather(self, nodes, feature_order=None):
+        self.init_topo()
+        nodes = nodes.to(self.current_device)
+        other = [d for c, devs in self.topo.p2pClique2Device.items() if c != self.current_clique for d in devs
+                 if self.shard_tensor_config.tensor_offset_device.get(d) is not None]
+        if not other:
+            return self.shard_tensor.gather(nodes, feature_order)
+        if feature_order is not None:
+            nodes = feature_order[nodes]
+        feature = self.shard_tensor.gather(nodes)
+        input_orders = torch.arange(nodes.size(0), dtype=torch.long, device=self.current_device)
+        wait_results = []
+        for inter_device in other:
+            self.collect_device(input_orders, nodes, inter_device, wait_results)
+        for orders, rows in wait_results:
+            feature[orders] = rows
+        return feature
+
+    @property
+    def shape(self):
+        return self.shard_tensor.shape()
+
+    @property
+    def device(self):
+        return self.current_device
+
+    def size(self, dim):
+        return self.shard_tensor.size(dim)
+
+    def share_ipc(self):
+        items = self.shard_tensor.share_ipc()
+        return [item.share_ipc() for item in items], self.cpu_tensor, self.shard_tensor_config
+
+    def from_ipc_handle(self, gpu_ipc_list, cpu_tensor):
+        for gpu_ipc in gpu_ipc_list:
+            item = torch_qv.ShardTensorItem()
+            item.from_ipc(gpu_ipc)
+            self.shard_tensor.append(item)
+        if cpu_tensor is not None:
+            self.cpu_tensor = cpu_tensor
+            self.shard_tensor.append(cpu_tensor, -1)
+
+    @classmethod
+    def new_from_share_ipc(cls, ipc_handles, current_device):
+        gpu_part_ipc_list, cpu_tensor, shard_tensor_config = ipc_handles
+        shard_tensor = cls(current_device, shard_tensor_config)
+        shard_tensor.from_ipc_handle(gpu_part_ipc_list, cpu_tensor)
+        return shard_tensor

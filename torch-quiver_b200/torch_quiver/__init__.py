@@ -1,0 +1,414 @@
+"""`torch_quiver` -- drop-in mirror of the reference's pybind11 extension module for the sampler + feature-gather hot
+path, implemented as a thin adapter over the C ABI of libquiver_b200.so (include/quiver_b200.h).
+
+Mirrored surface (reference: srcs/cpp/src/quiver/torch/module.cpp:16-26 and the register_* functions it calls):
+
+    device_quiver_from_csr_array(indptr, indices, edge_ids, device=0, cuda=False) -> Quiver   quiver_sample.cu:361,503
+    Quiver.sample_neighbor(stream_num, vertices, k) -> (neighbors, counts)                     quiver_sample.cu:113,507
+    Quiver.reindex_single(inputs, outputs, counts) -> (frontier, row_idx, col_idx)             quiver_sample.cu:305,511
+    Quiver.sample_sub(stream_num, vertices, k) -> (frontier, row_idx, col_idx)                 quiver_sample.cu:257,505
+    Quiver.cal_neighbor_prob(stream_num, last_prob, cur_prob, k)                               quiver_sample.cu:100,509
+    ShardTensor / ShardTensorItem / init_p2p / can_device_access_peer                          quiver_feature.cu:431-473
+
+PyTorch is used for device memory and streams only.  Deliberate deviations from the reference (SURVEY.md 8(b')):
+work is enqueued on torch's CURRENT stream (the reference sampler uses a private pool, quiver_sample.cu:116-117);
+CUDA errors raise RuntimeError instead of exit(1); invalid gather ids give zero rows instead of uninitialised memory;
+duplicate seeds are merged by reindex (the reference GPU path does too, its CPU path does not); shards are freed.
+CPU sampling (cpu_quiver_from_csr_array / CPUQuiver) is not part of this build: there is no CPU path at all.
+"""
+import ctypes
+import weakref
+from ctypes import byref, c_int, c_int64, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import QV_MAX_HOPS, QV_MAX_SHARDS, QuiverError, ShardTable, Unsupported, check, lib
+
+__all__ = [
+    "device_quiver_from_csr_array", "Quiver", "ShardTensor", "ShardTensorItem", "init_p2p", "can_device_access_peer",
+    "cpu_quiver_from_csr_array", "cpu_quiver_from_edge_index", "QuiverError",
+]
+
+
+def _stream(device):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr())
+
+
+def _check_long_cuda(t, name, device=None):
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.int64:
+        raise RuntimeError(f"{name} must be a torch.long tensor")  # reference: data_ptr<int64_t>() throws
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if device is not None and t.device.index != device:
+        raise RuntimeError(f"{name} is on cuda:{t.device.index} but this object lives on cuda:{device}")
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# peer access
+# ----------------------------------------------------------------------------------------------------------------------
+def can_device_access_peer(src_device_index, dst_device_index):
+    """torch_quiver.can_device_access_peer -- quiver_feature.cu:422-428."""
+    ok = c_int(0)
+    check(lib.qv_can_device_access_peer(int(src_device_index), int(dst_device_index), byref(ok)))
+    return bool(ok.value)
+
+
+def init_p2p(devices):
+    """torch_quiver.init_p2p -- quiver_feature.cu:378-421 (idempotent here)."""
+    devices = [int(d) for d in devices]
+    arr = (c_int * max(len(devices), 1))(*devices)
+    n = c_int(0)
+    check(lib.qv_init_p2p(arr, len(devices), byref(n)))
+    return n.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# sampler
+# ----------------------------------------------------------------------------------------------------------------------
+class Quiver:
+    """Device CSR + sampler scratch.  Mirrors `torch_quiver.Quiver` (class TorchQuiver, quiver_sample.cu:77-357)."""
+
+    def __init__(self, indptr, indices, device, cuda):
+        self.device = int(device)
+        self.rand_seed = 0  # the reference hard-codes 0 (quiver.cu.hpp:392); change it to draw a different sample
+        self._keep = []  # tensors whose memory the C object borrows
+        self._registered = None
+        self._handle = c_void_p()
+        if indptr.dim() != 1 or indices.dim() != 1:
+            raise RuntimeError("check_eq failed")  # reference: check_eq(dim, 1), quiver_sample.cu:373-376
+        if indptr.dtype != torch.int64 or indices.dtype != torch.int64:
+            raise RuntimeError("indptr / indices must be torch.long")
+        if indptr.numel() < 1:
+            raise RuntimeError("indptr must hold at least one entry")
+        dev = torch.device("cuda", self.device)
+        # indptr always lives in HBM (quiver_sample.cu:401-407)
+        indptr_d = indptr.to(dev).contiguous()
+        self._keep.append(indptr_d)
+        if cuda or indices.is_cuda:
+            indices_d = indices.to(dev).contiguous()
+            self._keep.append(indices_d)
+            indices_ptr = indices_d.data_ptr()
+        else:
+            # UVA / zero-copy: alias the caller's CPU tensor (quiver_sample.cu:413-421); the caller keeps it alive
+            indices_c = indices.contiguous()
+            self._keep.append(indices_c)
+            alias = c_void_p()
+            if indices_c.numel() > 0:
+                check(lib.qv_host_register(self.device, _ptr(indices_c), indices_c.numel() * 8, byref(alias)))
+                self._registered = indices_c
+            indices_ptr = alias.value or 0
+        self.node_count = indptr.numel() - 1
+        self.edge_count = indices.numel()
+        check(lib.qv_sampler_create(self.device, _ptr(indptr_d), self.node_count, c_void_p(indices_ptr),
+                                    self.edge_count, byref(self._handle)))
+        self._finalizer = weakref.finalize(self, Quiver._destroy, self._handle.value,
+                                           self._registered.data_ptr() if self._registered is not None else None)
+
+    @staticmethod
+    def _destroy(handle, registered_ptr):
+        if handle:
+            lib.qv_sampler_destroy(c_void_p(handle))
+        if registered_ptr:
+            lib.qv_host_unregister(c_void_p(registered_ptr))
+
+    # -- Quiver.sample_neighbor(stream_num, vertices, k) ------------------------------------------------------------
+    def sample_neighbor(self, stream_num, vertices, k):
+        v = _check_long_cuda(vertices, "vertices", self.device)
+        S = v.numel()
+        counts = torch.empty(S, dtype=torch.int64, device=v.device)
+        out_ptr = torch.empty(S, dtype=torch.int64, device=v.device)
+        total = c_int64(0)
+        st = _stream(self.device)
+        check(lib.qv_sample_count(self._handle, _ptr(v), S, int(k), _ptr(counts), _ptr(out_ptr), byref(total), st))
+        neighbors = torch.empty(total.value, dtype=torch.int64, device=v.device)
+        check(lib.qv_sample_fill(self._handle, _ptr(v), S, int(k), int(self.rand_seed), _ptr(out_ptr), _ptr(neighbors),
+                                 st))
+        return neighbors, counts
+
+    # -- Quiver.reindex_single(inputs, outputs, counts) -------------------------------------------------------------
+    def reindex_single(self, inputs, outputs, counts):
+        i = _check_long_cuda(inputs, "inputs", self.device)
+        o = _check_long_cuda(outputs, "outputs", self.device)
+        c = _check_long_cuda(counts, "counts", self.device)
+        S, tot = i.numel(), o.numel()
+        if c.numel() != S:
+            raise RuntimeError("counts must have one entry per input")
+        frontier = torch.empty(S + tot, dtype=torch.int64, device=i.device)
+        row_idx = torch.empty(tot, dtype=torch.int64, device=i.device)
+        col_idx = torch.empty(tot, dtype=torch.int64, device=i.device)
+        n_frontier = c_int64(0)
+        check(lib.qv_reindex(self._handle, _ptr(i), S, _ptr(o), tot, _ptr(c), _ptr(frontier), _ptr(row_idx),
+                             _ptr(col_idx), byref(n_frontier), _stream(self.device)))
+        return frontier[:n_frontier.value], row_idx, col_idx
+
+    # -- Quiver.sample_sub(stream_num, vertices, k) -----------------------------------------------------------------
+    def sample_sub(self, stream_num, vertices, k):
+        out, cnt = self.sample_neighbor(stream_num, vertices, k)
+        return self.reindex_single(vertices, out, cnt)
+
+    # -- Quiver.cal_neighbor_prob(stream_num, last_prob, cur_prob, k) -----------------------------------------------
+    def cal_neighbor_prob(self, stream_num, last_prob, cur_prob, k):
+        for t in (last_prob, cur_prob):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("cal_neighbor_prob expects contiguous float32 CUDA tensors")
+        check(lib.qv_cal_neighbor_prob(self._handle, _ptr(last_prob), _ptr(cur_prob), cur_prob.numel(), int(k),
+                                       _stream(self.device)))
+
+    # -- fused k-hop (ours): every hop enqueued back to back, one host synchronisation --------------------------------
+    def sample_khop(self, seeds, sizes):
+        """All hops of GraphSageSampler.sample (sage_sampler.py:118-147) in one C call.
+
+        Returns (n_id, [(edge_index[2, E_l], n_src_l, n_dst_l) for l in hops, innermost first]).
+        Raises `Unsupported` when a size is negative or the static bound is too large (callers fall back to the
+        per-hop calls)."""
+        v = _check_long_cuda(seeds, "seeds", self.device)
+        n_hops = len(sizes)
+        if not 1 <= n_hops <= QV_MAX_HOPS:
+            raise Unsupported(_lib.QV_ERR_UNSUPPORTED, f"{n_hops} hops")
+        S = v.numel()
+        sz = (c_int64 * n_hops)(*[int(s) for s in sizes])
+        bn = (c_int64 * (n_hops + 1))()
+        be = (c_int64 * n_hops)()
+        check(lib.qv_khop_bounds(S, sz, n_hops, bn, be))
+        n_id = torch.empty(max(bn[n_hops], 1), dtype=torch.int64, device=v.device)
+        bufs = [torch.empty(max(2 * be[h], 1), dtype=torch.int64, device=v.device) for h in range(n_hops)]
+        buf_ptrs = (c_void_p * n_hops)(*[b.data_ptr() for b in bufs])
+        out_nodes = (c_int64 * (n_hops + 1))()
+        out_edges = (c_int64 * n_hops)()
+        check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), _ptr(n_id), buf_ptrs, out_nodes,
+                          out_edges, _stream(self.device)))
+        hops = []
+        for h in range(n_hops):
+            E = out_edges[h]
+            hops.append((bufs[h][:2 * E].view(2, E), out_nodes[h + 1], out_nodes[h]))
+        return n_id[:out_nodes[n_hops]], hops
+
+
+def device_quiver_from_csr_array(indptr, indices, edge_ids=None, device=0, cuda=False):
+    """torch_quiver.device_quiver_from_csr_array -- quiver_sample.cu:361-461.  `edge_ids` is accepted and ignored:
+    the reference plumbs it but every sampler returns an empty e_id (sage_sampler.py:143)."""
+    return Quiver(indptr, indices, device, cuda)
+
+
+def cpu_quiver_from_csr_array(*_args, **_kwargs):
+    raise NotImplementedError("the B200 build has no CPU sampling path (reference: srcs/cpp/src/quiver/quiver.cpp); "
+                              "use mode='GPU' or mode='UVA'")
+
+
+cpu_quiver_from_edge_index = cpu_quiver_from_csr_array
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# feature shards
+# ----------------------------------------------------------------------------------------------------------------------
+_ELEMENT_DTYPE = {1: torch.uint8, 2: torch.float16, 4: torch.float32, 8: torch.float64}  # quiver_feature.cu:262-267
+
+
+def _pitch_for(row_bytes):
+    return (row_bytes + 15) // 16 * 16
+
+
+class ShardTensorItem:
+    """CUDA-IPC carrier of one GPU shard -- class ShardTensorItem, quiver_feature.cu:20-55."""
+
+    def __init__(self):
+        self.device = -1
+        self.element_size = 4
+        self.mem_handle = b"\0" * _lib.QV_IPC_HANDLE_BYTES
+        self.shape = []
+
+    def share_ipc(self):
+        return self.device, self.element_size, self.mem_handle, list(self.shape)
+
+    def from_ipc(self, ipc_data):
+        self.device, self.element_size, handle, shape = ipc_data
+        self.mem_handle = bytes(handle)
+        self.shape = list(shape)
+
+
+class _Shard:
+    __slots__ = ("device", "ptr", "rows", "pitch", "owned", "ipc_opened", "host_tensor", "shape")
+
+    def __init__(self, device, ptr, rows, pitch, owned=False, ipc_opened=False, host_tensor=None, shape=None):
+        self.device, self.ptr, self.rows, self.pitch = device, ptr, rows, pitch
+        self.owned, self.ipc_opened, self.host_tensor, self.shape = owned, ipc_opened, host_tensor, shape
+
+
+class ShardTensor:
+    """Row-sharded feature table readable from one GPU -- class ShardTensor, quiver_feature.cu:57-376.
+
+    Shards are appended in row order; shard s holds rows [offset[s], offset[s+1]).  device >= 0: rows are copied into
+    that GPU's HBM (padded to a 16-byte pitch) and read in the gather kernel through a peer-mapped pointer;
+    device == -1: the caller's CPU tensor is registered and read zero-copy over PCIe (it is aliased, not copied --
+    keep it alive, as with the reference)."""
+
+    def __init__(self, device):
+        self.device_ = int(device)
+        self.shards = []
+        self.offset_list_ = [0]
+        self.shape_ = []
+        self.element_size = 4
+        self.dtype = None
+        self.gather_variant = 0
+        self._finalizer = weakref.finalize(self, ShardTensor._release, self.shards)
+
+    @staticmethod
+    def _release(shards):
+        for sh in shards:
+            try:
+                if sh.owned and sh.ptr:
+                    lib.qv_free(sh.device, c_void_p(sh.ptr))
+                elif sh.ipc_opened and sh.ptr:
+                    lib.qv_ipc_close_handle(sh.device, c_void_p(sh.ptr))
+            except Exception:  # interpreter shutdown
+                pass
+        shards.clear()
+
+    # -- bookkeeping shared by both append flavours -----------------------------------------------------------------
+    def _admit(self, shape, element_size, dtype):
+        shape = [int(x) for x in shape]
+        if len(shape) < 1:
+            raise RuntimeError("a shard needs at least one dimension")
+        if not self.shape_:
+            self.shape_ = [0] + shape[1:]
+            self.element_size = int(element_size)
+            self.dtype = dtype
+        elif shape[1:] != self.shape_[1:] or int(element_size) != self.element_size:
+            raise RuntimeError(f"shard shape {shape} / element size {element_size} does not match "
+                               f"{self.shape_} / {self.element_size}")
+        if len(self.shards) >= QV_MAX_SHARDS:
+            raise RuntimeError(f"at most {QV_MAX_SHARDS} shards per ShardTensor")
+        self.shape_[0] += shape[0]
+        self.offset_list_.append(self.offset_list_[-1] + shape[0])
+
+    def _row_bytes(self):
+        return self.stride(0) * self.element_size
+
+    def append(self, item, target_device=None):
+        if isinstance(item, ShardTensorItem):
+            return self._append_item(item)
+        return self._append_tensor(item, int(target_device))
+
+    def _append_tensor(self, tensor, target_device):
+        if tensor.is_cuda:
+            raise RuntimeError("tensor must be CPU tensor")  # CHECK_CPU, quiver_feature.cu:19,147
+        tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
+        self._admit(tensor.shape, tensor.element_size(), tensor.dtype)
+        rows, row_bytes = tensor.shape[0], self._row_bytes()
+        if target_device >= 0:
+            pitch = _pitch_for(row_bytes)
+            ptr = c_void_p()
+            check(lib.qv_malloc(target_device, max(rows * pitch, 16), byref(ptr)))
+            check(lib.qv_upload_rows(target_device, ptr, pitch, _ptr(tensor), row_bytes, row_bytes, rows))
+            if target_device != self.device_ and can_device_access_peer(self.device_, target_device):
+                init_p2p([self.device_, target_device])
+            self.shards.append(_Shard(target_device, ptr.value, rows, pitch, owned=True, shape=list(tensor.shape)))
+        else:
+            alias = c_void_p()
+            if tensor.numel() > 0:
+                check(lib.qv_host_register(self.device_, _ptr(tensor), tensor.numel() * tensor.element_size(),
+                                           byref(alias)))
+            self.shards.append(_Shard(-1, alias.value or 0, rows, row_bytes, host_tensor=tensor,
+                                      shape=list(tensor.shape)))
+
+    def _append_item(self, item):
+        self._admit(item.shape, item.element_size, _ELEMENT_DTYPE.get(int(item.element_size)))
+        row_bytes = self._row_bytes()
+        ptr = c_void_p()
+        handle = (ctypes.c_ubyte * _lib.QV_IPC_HANDLE_BYTES).from_buffer_copy(bytes(item.mem_handle))
+        # open in the context of the device that will dereference it (quiver_feature.cu:122-134)
+        check(lib.qv_ipc_open_handle(self.device_, handle, byref(ptr)))
+        self.shards.append(_Shard(int(item.device), ptr.value, int(item.shape[0]), _pitch_for(row_bytes),
+                                  ipc_opened=True, shape=list(item.shape)))
+
+    # -- ShardTensor.__getitem__(indices) ---------------------------------------------------------------------------
+    def _table(self, current_device):
+        t = ShardTable()
+        t.n_shards = len(self.shards)
+        for s, sh in enumerate(self.shards):
+            t.row_begin[s] = self.offset_list_[s]
+            t.ptr[s] = sh.ptr
+            t.pitch[s] = sh.pitch
+            t.accessible[s] = 1 if (sh.device < 0 or sh.device == current_device
+                                    or can_device_access_peer(current_device, sh.device)) else 0
+        t.row_begin[len(self.shards)] = self.offset_list_[-1]
+        return t
+
+    def gather(self, indices, feature_order=None, out=None):
+        """`self[indices]` with the optional `feature_order[idx]` indirection folded into the kernel."""
+        if not self.shards:
+            raise RuntimeError("ShardTensor is empty")
+        idx = _check_long_cuda(indices, "indices")
+        current = idx.device.index
+        n = idx.numel()
+        dtype = self.dtype or _ELEMENT_DTYPE.get(self.element_size)
+        if dtype is None:
+            raise RuntimeError(f"unsupported element size {self.element_size}")
+        if out is None:
+            out = torch.empty([n] + self.shape_[1:], dtype=dtype, device=idx.device)
+        order_ptr = c_void_p(0)
+        if feature_order is not None:
+            fo = _check_long_cuda(feature_order, "feature_order", current)
+            order_ptr = _ptr(fo)
+        key = current
+        cache = getattr(self, "_table_cache", None)
+        if cache is None or cache[0] != (key, len(self.shards)):
+            self._table_cache = ((key, len(self.shards)), self._table(current))
+        table = self._table_cache[1]
+        with torch.cuda.device(current):
+            check(lib.qv_gather(byref(table), _ptr(idx), order_ptr, n, self._row_bytes(), _ptr(out),
+                                int(self.gather_variant), _stream(current)))
+        return out
+
+    def __getitem__(self, indices):
+        return self.gather(indices)
+
+    # -- introspection (quiver_feature.cu:304-333, 352) -------------------------------------------------------------
+    def shape(self):
+        return list(self.shape_)
+
+    def device(self):
+        return self.device_
+
+    def size(self, dim):
+        return self.shape_[dim] if self.shape_ else 0
+
+    def stride(self, dim):
+        res = 1
+        for d in self.shape_[dim + 1:]:
+            res *= d
+        return res
+
+    def numel(self):
+        res = 1
+        for d in self.shape_:
+            res *= d
+        return res
+
+    def device_count(self):
+        return len(self.shards)
+
+    def share_ipc(self):
+        """One ShardTensorItem per GPU shard (quiver_feature.cu:335-350); the host tier travels separately."""
+        items = []
+        for sh in self.shards:
+            if sh.device < 0:
+                continue
+            if not sh.owned:
+                raise RuntimeError("only the process that created a GPU shard can export it")
+            handle = (ctypes.c_ubyte * _lib.QV_IPC_HANDLE_BYTES)()
+            check(lib.qv_ipc_get_handle(sh.device, c_void_p(sh.ptr), handle))
+            item = ShardTensorItem()
+            item.device, item.element_size, item.mem_handle, item.shape = sh.device, self.element_size, bytes(handle), \
+                list(sh.shape)
+            items.append(item)
+        return items
+
+    def unregister(self, cpu_tensor):
+        check(lib.qv_host_unregister(_ptr(cpu_tensor)))
