@@ -1,0 +1,179 @@
+"""GPU parity, feature gather: 0 ULP (pure byte copy) against the oracle and against `tensor[idx]`, which is the
+reference's own assertion (tests/python/cuda/test_features.py:339,364,421; test_shard_tensor.py:77,106), across
+dtypes, row sizes (16-byte clean and not), tiers, invalid ids, the folded feature_order, both kernel variants, and
+the full quiver.Feature API incl. mp.spawn IPC."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(n, d, dtype, seed=0):
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy(rng.integers(0, 10, (n, d)).astype(np.float32)).to(dtype)  # test_features.py:310-313
+
+
+def _np(t):
+    return t.view(torch.int16).numpy() if t.dtype in (torch.float16, torch.bfloat16) else t.numpy()
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("d", [100, 128, 256, 602, 768, 1, 3, 17, 600])
+def test_single_shard_matches_oracle_and_indexing(oracle, d, dtype, variant):
+    import torch_quiver as qv
+    n, m = 20000, 30011
+    x = _mk(n, d, dtype, seed=d)
+    if variant == 2 and (d * x.element_size()) % 16 != 0:
+        pytest.skip("TMA variant needs 16-byte rows")
+    st = qv.ShardTensor(0)
+    st.gather_variant = variant
+    st.append(x, 0)
+    idx = torch.from_numpy(np.random.default_rng(1).integers(0, n, m))
+    got = st[idx.cuda()]
+    assert got.shape == (m, d) and got.dtype == dtype and got.is_cuda and got.is_contiguous()
+    assert torch.equal(got.cpu(), x[idx])
+    want = oracle.gather([_np(x)], idx.numpy())
+    assert np.array_equal(_np(got.cpu()), want)
+    assert st.shape() == [n, d] and st.size(0) == n and st.size(1) == d and st.numel() == n * d
+    assert st.stride(0) == d and st.device() == 0 and st.device_count() == 1
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("d,dtype", [(128, torch.float32), (602, torch.float32), (600, torch.float16), (100, torch.float32)])
+def test_tiers_hbm_shards_plus_pinned_host(oracle, d, dtype, variant):
+    import torch_quiver as qv
+    if variant == 2 and (d * torch.empty(0, dtype=dtype).element_size()) % 16 != 0:
+        pytest.skip("TMA variant needs 16-byte rows")
+    n = 12000
+    x = _mk(n, d, dtype, seed=3)
+    cuts = [0, 5000, 5001, 9000, n]  # two real HBM shards, a 1-row shard, and the zero-copy host tier
+    st = qv.ShardTensor(0)
+    st.gather_variant = variant
+    host_part = x[cuts[3]:].clone()
+    for a, b in zip(cuts[:3], cuts[1:4]):
+        st.append(x[a:b], 0)
+    st.append(host_part, -1)
+    assert st.device_count() == 4 and st.size(0) == n
+    rng = np.random.default_rng(5)
+    idx = np.concatenate([rng.integers(0, n, 9000), np.array(cuts[:-1]), np.array(cuts[1:]) - 1])
+    got = st[torch.from_numpy(idx).cuda()]
+    assert torch.equal(got.cpu(), x[idx])
+    parts = [_np(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(_np(got.cpu()), oracle.gather(parts, idx))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_invalid_ids_give_zero_rows_and_feature_order_is_folded(oracle, variant):
+    import torch_quiver as qv
+    n, d = 5000, 64
+    x = _mk(n, d, torch.float32, seed=9) + 1.0  # no zero rows in the table
+    st = qv.ShardTensor(0)
+    st.gather_variant = variant
+    st.append(x[:3000], 0)
+    st.append(x[3000:].clone(), -1)
+    idx = np.array([0, -1, n, n - 1, 2**40, -2**40, 2999, 3000], dtype=np.int64)
+    got = st[torch.from_numpy(idx).cuda()].cpu()
+    want = oracle.gather([x[:3000].numpy(), x[3000:].numpy()], idx)
+    assert np.array_equal(got.numpy(), want)
+    assert not got[[1, 2, 4, 5]].any() and torch.equal(got[[0, 3, 6, 7]], x[[0, n - 1, 2999, 3000]])
+    order = torch.from_numpy(np.random.default_rng(0).permutation(n))
+    ids = torch.from_numpy(np.random.default_rng(1).integers(0, n, 7777))
+    got = st.gather(ids.cuda(), order.cuda())
+    assert torch.equal(got.cpu(), x[order[ids]])
+    assert np.array_equal(got.cpu().numpy(),
+                          oracle.gather([x[:3000].numpy(), x[3000:].numpy()], ids.numpy(), order.numpy()))
+    # empty request
+    assert st[torch.empty(0, dtype=torch.long, device="cuda")].shape == (0, d)
+
+
+def test_large_output_beyond_4gib_offsets():
+    """The reference's unsigned 32-bit `warp_start * stride` wraps once the output exceeds 4 GiB
+    (shard_tensor.cu.hpp:53); here every offset is 64-bit.  1.5 M rows x 3072 B = 4.6 GB."""
+    import torch_quiver as qv
+    n, d = 100000, 768
+    x = torch.randn(n, d)
+    st = qv.ShardTensor(0)
+    st.append(x, 0)
+    m = 1_500_000
+    idx = torch.randint(0, n, (m, ), device="cuda")
+    got = st[idx]
+    xd = x.cuda()
+    for lo in (0, m // 2, m - 4096):
+        assert torch.equal(got[lo:lo + 4096], xd[idx[lo:lo + 4096]])
+    assert torch.equal(got[-1], xd[idx[-1]])
+
+
+@pytest.mark.parametrize("policy,cache", [("device_replicate", "2M"), ("p2p_clique_replicate", "1M"),
+                                          ("device_replicate", 0), ("device_replicate", "1G")])
+def test_feature_api_matches_tensor_indexing(policy, cache):
+    import quiver
+    from graphs import powerlaw_csr
+    n, d = 30000, 100
+    indptr, indices = powerlaw_csr(n, 10.0, seed=4)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    x = torch.randn(n, d)
+    quiver.init_p2p([0])
+    f = quiver.Feature(rank=0, device_list=[0], device_cache_size=cache, cache_policy=policy, csr_topo=topo)
+    f.from_cpu_tensor(x)
+    assert f.shape == [n, d] and f.size(0) == n and f.size(1) == d and f.dim() == 2
+    idx = torch.randint(0, n, (80000, ))
+    res = f[idx.cuda()]
+    assert res.is_cuda and res.device.index == 0
+    assert torch.equal(res.cpu(), x[idx])  # original ids in, original rows out: feature_order is hidden
+    assert torch.equal(f[idx].cpu(), x[idx])  # CPU indices are moved to the rank, as the reference does
+    xh = x.half()
+    fh = quiver.Feature(rank=0, device_list=[0], device_cache_size=cache, cache_policy=policy)
+    fh.from_cpu_tensor(xh)
+    assert torch.equal(fh[idx.cuda()].cpu(), xh[idx])
+
+
+def _ipc_child(rank, feature, sampler, x, indptr, indices, seeds, want_nid, ok):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "torch-quiver_b200")]
+    torch.cuda.set_device(0)
+    idx = torch.randint(0, x.shape[0], (20000, ), device="cuda")
+    res = feature[idx]  # lazy_init_from_ipc_handle: opens the parent's shards through CUDA IPC
+    good = torch.equal(res.cpu(), x[idx.cpu()])
+    n_id, bs, adjs = sampler.sample(seeds)  # lazy_init_quiver in the child
+    good = good and torch.equal(n_id.cpu(), want_nid) and bs == seeds.numel() and len(adjs) == 2
+    ok[rank] = 1 if good else 0
+
+
+def test_feature_and_sampler_cross_mp_spawn():
+    """examples/multi_gpu/pyg/ogb-products/dist_sampling_ogb_products_quiver.py:158-163: Feature and sampler are
+    handed to mp.spawn workers; GPU shards travel as CUDA IPC handles, the cold tier as shared memory."""
+    import quiver
+    import torch.multiprocessing as mp
+    from graphs import powerlaw_csr
+    n, d = 20000, 128
+    indptr, indices = powerlaw_csr(n, 8.0, seed=6)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    x = torch.randn(n, d)
+    feature = quiver.Feature(rank=0, device_list=[0], device_cache_size="4M", cache_policy="device_replicate",
+                             csr_topo=topo)
+    feature.from_cpu_tensor(x)
+    sampler = quiver.pyg.GraphSageSampler(topo, [10, 5], device=0, mode="GPU")
+    seeds = torch.arange(500, 756)
+    want_nid, _, _ = sampler.sample(seeds)
+    ok = torch.zeros(2, dtype=torch.int32).share_memory_()
+    mp.spawn(_ipc_child, args=(feature, sampler, x, indptr, indices, seeds, want_nid.cpu(), ok), nprocs=2, join=True)
+    assert ok.tolist() == [1, 1]
+
+
+def test_shards_are_freed():
+    import torch_quiver as qv
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(3):
+        st = qv.ShardTensor(0)
+        st.append(torch.zeros(200000, 256), 0)  # 205 MB
+        st[torch.arange(10, device="cuda")]
+        del st
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 100 * 2**20  # the reference never frees shards (no destructor): SURVEY.md 8(b)

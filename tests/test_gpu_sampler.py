@@ -1,0 +1,253 @@
+"""GPU parity, sampler: the CUDA path (through the C ABI) must equal the oracle BIT FOR BIT -- counts, sampled ids
+under the reference's generator seed, reindex outputs, the fused k-hop -- plus structural / property checks at
+BASELINE.json sizes where the CPU oracle would take too long."""
+import numpy as np
+import pytest
+import torch
+
+from graphs import MINI, powerlaw_csr, simple_graph
+
+pytestmark = pytest.mark.gpu
+
+
+def _quiver(indptr, indices, cuda=True, device=0):
+    import torch_quiver as qv
+    return qv.device_quiver_from_csr_array(torch.from_numpy(indptr), torch.from_numpy(indices),
+                                           torch.zeros(1, dtype=torch.long), device, cuda)
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).cuda()
+
+
+@pytest.fixture(scope="module")
+def g2k():
+    return powerlaw_csr(2000, 30.0, seed=7)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 25, 33, 64, 2000, -1])
+@pytest.mark.parametrize("S", [1, 63, 64, 65, 1000])
+def test_sample_neighbor_bit_exact(oracle, g2k, k, S):
+    indptr, indices = g2k
+    q = _quiver(indptr, indices)
+    seeds = np.random.default_rng(S * 131 + k).integers(0, 2000, S)
+    out, cnt = q.sample_neighbor(0, _dev(seeds), k)
+    ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, k)
+    assert cnt.cpu().numpy().tolist() == ref_cnt.tolist()
+    assert out.cpu().numpy().tolist() == ref_out.tolist()
+    assert out.dtype == torch.int64 and out.is_cuda and cnt.shape == (S, )
+
+
+def test_sample_heavy_tail_and_large_fanout(oracle):
+    # hub rows far above k (long reservoir loops), fan-outs beyond the shared-memory slot limit (1024)
+    indptr, indices = powerlaw_csr(6000, 120.0, seed=8, alpha=1.3)
+    assert np.diff(indptr).max() > 3000
+    q = _quiver(indptr, indices)
+    seeds = np.argsort(-np.diff(indptr))[:200].copy()  # the 200 biggest hubs
+    for k in (10, 1024, 1025, 1500):
+        out, cnt = q.sample_neighbor(0, _dev(seeds), k)
+        ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, k)
+        assert torch.equal(cnt.cpu(), torch.from_numpy(ref_cnt))
+        assert torch.equal(out.cpu(), torch.from_numpy(ref_out)), k
+        assert oracle.validate_sample(indptr, indices, seeds, k, ref_cnt, out.cpu().numpy()) == 0
+
+
+def test_many_blocks_and_other_seeds(oracle):
+    # > 1024 blocks of 64 seeds: grows the XORWOW state cache; rand_seed != 0 uses per-launch states
+    indptr, indices = powerlaw_csr(50000, 12.0, seed=9)
+    q = _quiver(indptr, indices)
+    seeds = np.random.default_rng(3).integers(0, 50000, 70000)
+    out, cnt = q.sample_neighbor(0, _dev(seeds), 4)
+    ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, 4)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref_out)) and torch.equal(cnt.cpu(), torch.from_numpy(ref_cnt))
+    small = seeds[:3000]
+    for rs in (1, 12345, 2**40 + 3):
+        q.rand_seed = rs
+        out, _ = q.sample_neighbor(0, _dev(small), 4)
+        ref_out, _ = oracle.sample_neighbor(indptr, indices, small, 4, rand_seed=rs)
+        assert torch.equal(out.cpu(), torch.from_numpy(ref_out)), rs
+    q.rand_seed = 0
+    out2, _ = q.sample_neighbor(0, _dev(small), 4)
+    ref2, _ = oracle.sample_neighbor(indptr, indices, small, 4)
+    assert torch.equal(out2.cpu(), torch.from_numpy(ref2))
+
+
+def test_edge_cases(oracle, g2k):
+    indptr, indices = g2k
+    q = _quiver(indptr, indices)
+    # empty seed list (the reference launches a 0-block grid: quiver.cu.hpp:388)
+    out, cnt = q.sample_neighbor(0, torch.empty(0, dtype=torch.long, device="cuda"), 5)
+    assert out.numel() == 0 and cnt.numel() == 0
+    f, r, c = q.reindex_single(torch.empty(0, dtype=torch.long, device="cuda"), out, cnt)
+    assert f.numel() == 0 and r.numel() == 0 and c.numel() == 0
+    # isolated seeds only
+    iso = np.nonzero(np.diff(indptr) == 0)[0][:10]
+    assert len(iso) > 0
+    out, cnt = q.sample_neighbor(0, _dev(iso), 5)
+    assert out.numel() == 0 and cnt.sum().item() == 0
+    f, r, c = q.reindex_single(_dev(iso), out, cnt)
+    assert f.cpu().tolist() == iso.tolist()
+    # k = 0, out-of-range seeds (defined here as degree 0), wrong dtype / device
+    out, cnt = q.sample_neighbor(0, _dev([1, 2, 3]), 0)
+    assert out.numel() == 0
+    out, cnt = q.sample_neighbor(0, _dev([-5, 2000, 10**12, 3]), 5)
+    assert cnt.cpu().tolist()[:3] == [0, 0, 0]
+    with pytest.raises(RuntimeError):
+        q.sample_neighbor(0, torch.tensor([1, 2], dtype=torch.int32, device="cuda"), 2)
+    with pytest.raises(RuntimeError):
+        q.sample_neighbor(0, torch.tensor([1, 2]), 2)
+
+
+def test_mini_known_answer_on_gpu():
+    m = MINI
+    q = _quiver(np.array(m["indptr"]), np.array(m["indices"]))
+    out, cnt = q.sample_neighbor(0, _dev(m["seeds"]), m["k"])
+    assert cnt.cpu().tolist() == m["counts"]
+    assert out.cpu().tolist()[4:6] == [0, 2]  # seed 1 has deg 2 <= k: verbatim CSR row
+    f, r, c = q.reindex_single(_dev(m["seeds"]), _dev(m["draw"]), _dev(m["counts"]))
+    assert (f.cpu().tolist(), r.cpu().tolist(), c.cpu().tolist()) == (m["frontier"], m["row_idx"], m["col_idx"])
+
+
+@pytest.mark.parametrize("n,nbr,k", [(10, 5, 10), (100, 10, 5), (1000, 10, 10)])  # tests/cpp/test_quiver_cpu.cpp:70-75
+def test_reference_structural_cases_on_gpu(oracle, n, nbr, k):
+    indptr, indices = simple_graph(n, nbr)
+    q = _quiver(indptr, indices)
+    seeds = np.arange(n)
+    out, cnt = q.sample_neighbor(0, _dev(seeds), k)
+    assert oracle.validate_sample(indptr, indices, seeds, k, cnt.cpu().numpy(), out.cpu().numpy()) == 0
+
+
+def test_reindex_bit_exact(oracle, golden_dir):
+    import json
+    import os
+    rng = np.random.default_rng(4)
+    q = _quiver(*powerlaw_csr(100, 3.0, seed=1))
+    # reference CPU extension's own outputs (unique seeds)
+    kat = json.load(open(os.path.join(golden_dir, "ref_cpu_kat.json")))
+    for c in kat["cases"]:
+        f, r, col = q.reindex_single(_dev(c["seeds"]), _dev(c["draw"]), _dev(c["counts"]))
+        assert f.cpu().tolist() == c["frontier"] and r.cpu().tolist() == c["row_idx"]
+        assert col.cpu().tolist() == c["col_idx"]
+    # random, heavy duplication, duplicate seeds (GPU semantics: merged), sizes across scan-tile boundaries
+    for S, tot_per in [(1, 3), (1023, 1), (1024, 2), (1025, 7), (5000, 25), (40000, 10)]:
+        seeds = rng.integers(0, max(S // 2, 2), S)
+        counts = rng.integers(0, tot_per + 1, S)
+        outputs = rng.integers(0, max(S, 50), int(counts.sum()))
+        f, r, col = q.reindex_single(_dev(seeds), _dev(outputs), _dev(counts))
+        of, orow, ocol = oracle.reindex(seeds, outputs, counts)
+        assert torch.equal(f.cpu(), torch.from_numpy(of)), S
+        assert torch.equal(r.cpu(), torch.from_numpy(orow)), S
+        assert torch.equal(col.cpu(), torch.from_numpy(ocol)), S
+
+
+@pytest.mark.parametrize("sizes", [[25, 10], [15, 10, 5], [3], [2, 2, 2, 2], [40, 0, 3]])
+def test_fused_khop_equals_oracle_and_per_hop(oracle, sizes):
+    import quiver
+    indptr, indices = powerlaw_csr(20000, 25.0, seed=10)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, sizes, device=0, mode="GPU")
+    seeds = np.random.default_rng(len(sizes)).permutation(20000)[:512]
+    n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+    o_nid, o_bs, o_adjs = oracle.khop(indptr, indices, seeds, sizes)
+    assert bs == o_bs == 512
+    assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+    assert len(adjs) == len(sizes)
+    for adj, (o_ei, o_size) in zip(adjs, o_adjs):
+        assert adj.edge_index.is_contiguous() and adj.edge_index.shape == (2, o_ei.shape[1])
+        assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei))
+        assert adj.size.tolist() == list(o_size) and not adj.size.is_cuda
+        assert adj.e_id.numel() == 0
+    assert torch.equal(n_id[:bs].cpu(), torch.from_numpy(seeds))  # targets come first
+    # the per-hop path (what the reference's Python loop does) gives the same answer
+    sampler.fused = False
+    n_id2, _, adjs2 = sampler.sample(torch.from_numpy(seeds))
+    assert torch.equal(n_id2, n_id)
+    for a, b in zip(adjs, adjs2):
+        assert torch.equal(a.edge_index, b.edge_index) and a.size.tolist() == b.size.tolist()
+
+
+def test_full_neighbourhood_hop_falls_back(oracle):
+    import quiver
+    indptr, indices = powerlaw_csr(3000, 10.0, seed=12)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [5, -1], device=0, mode="GPU")
+    seeds = np.arange(100, 228)
+    n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+    o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [5, 3000])
+    assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+    assert torch.equal(adjs[0].edge_index.cpu(), torch.from_numpy(o_adjs[0][0]))
+
+
+def test_uva_mode_reads_host_indices(oracle, g2k):
+    indptr, indices = g2k
+    q = _quiver(indptr, indices, cuda=False)  # indices stay in (registered) host memory
+    seeds = np.random.default_rng(0).integers(0, 2000, 500)
+    out, cnt = q.sample_neighbor(0, _dev(seeds), 10)
+    ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, 10)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref_out)) and torch.equal(cnt.cpu(), torch.from_numpy(ref_cnt))
+
+
+def test_non_default_stream_is_respected(oracle, g2k):
+    indptr, indices = g2k
+    q = _quiver(indptr, indices)
+    seeds = np.random.default_rng(1).integers(0, 2000, 4096)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        d = _dev(seeds)
+        out, cnt = q.sample_neighbor(0, d, 7)
+        f, r, c = q.reindex_single(d, out, cnt)
+    s.synchronize()
+    ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, 7)
+    of, _, ocol = oracle.reindex(seeds, ref_out, ref_cnt)
+    assert torch.equal(out.cpu(), torch.from_numpy(ref_out))
+    assert torch.equal(f.cpu(), torch.from_numpy(of)) and torch.equal(c.cpu(), torch.from_numpy(ocol))
+
+
+def test_cal_neighbor_prob(oracle):
+    indptr, indices = powerlaw_csr(5000, 9.0, seed=13)
+    q = _quiver(indptr, indices)
+    p = np.random.default_rng(2).random(5000).astype(np.float32)
+    cur = torch.zeros(5000, device="cuda")
+    q.cal_neighbor_prob(0, torch.from_numpy(p).cuda(), cur, 4)
+    want = oracle.cal_next(p, 4, indptr, indices)
+    # fp32, same operation order; the only licence is FMA contraction of 1 - (1-p)*acc on the GPU (<= 1 ulp of 1.0)
+    assert np.abs(cur.cpu().numpy() - want).max() <= 1.2e-7
+
+
+def test_products_scale_properties():
+    """BASELINE config 1 (ogbn-products-shaped: 2.45 M nodes, ~124 M edges, fan-out [15,10,5]) -- size-independent
+    properties checked on the device: counts == min(deg,k); every sampled id is a neighbour of its seed; no position is
+    picked twice; frontier is duplicate-free, starts with the seeds, and edge_index indexes inside it."""
+    import quiver
+    N = 2_449_029
+    g = torch.Generator(device="cuda").manual_seed(0)
+    raw = (1.0 - torch.rand(N, generator=g, device="cuda", dtype=torch.float64)).pow(-0.5)
+    deg = (raw * (50.5 / raw.mean())).floor().long().clamp_(max=N - 1)
+    indptr = torch.zeros(N + 1, dtype=torch.long, device="cuda")
+    indptr[1:] = deg.cumsum(0)
+    E = int(indptr[-1])
+    row = torch.repeat_interleave(torch.arange(N, device="cuda"), deg)
+    col = torch.randint(0, N, (E, ), generator=g, device="cuda")
+    key, _ = torch.sort(row * N + col)  # CSR with sorted columns, as one flat sorted key array
+    indices = key % N
+    del row, col
+    topo = quiver.CSRTopo(indptr=indptr.cpu(), indices=indices.cpu())
+    sampler = quiver.pyg.GraphSageSampler(topo, [15, 10, 5], device=0, mode="GPU")
+    seeds = torch.randperm(N, generator=g, device="cuda")[:1024]
+    n_id, bs, adjs = sampler.sample(seeds)
+    assert torch.equal(n_id[:bs], seeds)
+    assert torch.unique(n_id).numel() == n_id.numel()
+    n_dst = bs
+    for adj, k in zip(adjs[::-1], [15, 10, 5]):
+        src, dst = adj.edge_index[0], adj.edge_index[1]
+        assert adj.size.tolist()[1] == n_dst
+        assert int(src.max()) < adj.size[0] and int(dst.max()) < n_dst
+        cnt = torch.bincount(dst, minlength=n_dst)
+        assert torch.equal(cnt, deg[n_id[:n_dst]].clamp(max=k))
+        assert bool((dst[1:] >= dst[:-1]).all())  # per-seed blocks are contiguous and in seed order
+        # membership: (target node, source node) must be an edge
+        ekey = n_id[dst] * N + n_id[src]
+        pos = torch.searchsorted(key, ekey)
+        assert bool((key[pos.clamp(max=E - 1)] == ekey).all())
+        n_dst = int(adj.size[0])
+    assert n_dst == n_id.numel()

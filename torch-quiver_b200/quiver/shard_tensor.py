@@ -143,3 +143,48 @@ class ShardTensor:
         shard_tensor = cls(current_device, shard_tensor_config)
         shard_tensor.from_ipc_handle(gpu_part_ipc_list, cpu_tensor)
         return shard_tensor
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# One process per GPU (torchrun) placement: every rank contributes one HBM shard, handles travel over torch.distributed
+# ----------------------------------------------------------------------------------------------------------------------
+def exchange_shard_items(local_item, group=None):
+    """all_gather the (device, element_size, handle, shape) tuples of every rank's shard, in rank order.
+
+    Control-plane only (a few hundred bytes per rank, any backend incl. gloo); the data path stays one-sided peer
+    loads inside the gather kernel.  The reference ships the same tuples through ForkingPickler
+    (srcs/python/quiver/multiprocessing/reductions.py:5-33); this is the torch.distributed equivalent."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    items = [None] * world
+    dist.all_gather_object(items, local_item, group=group)
+    return items
+
+
+def build_from_ranks(local_rows, device, group=None, cpu_part=None):
+    """Row-shard a feature table over the ranks of `group`: rank r's `local_rows` ([n_r, D] CPU tensor) become shard r
+    in that rank's HBM; every rank maps all peers' shards through CUDA IPC and can gather any row one-sidedly over
+    NVLink.  Optional `cpu_part`: cold rows appended as the pinned-host tier.  Returns a quiver ShardTensor."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    st = ShardTensor(device, ShardTensorConfig({}))
+    # place the local shard first to obtain its handle, then rebuild the table in rank order
+    local = torch_qv.ShardTensor(device)
+    local.append(local_rows, device)
+    items = exchange_shard_items(local.share_ipc()[0].share_ipc(), group)
+    start = 0
+    for r, ipc in enumerate(items):
+        rows = ipc[3][0]
+        if r == rank:
+            st.shard_tensor.adopt(local)
+        else:
+            item = torch_qv.ShardTensorItem()
+            item.from_ipc(ipc)
+            st.shard_tensor.append(item)
+        st.shard_tensor_config.tensor_offset_device[ipc[0]] = Offset(start, start + rows)
+        start += rows
+    if cpu_part is not None and cpu_part.numel() > 0:
+        st.cpu_tensor = cpu_part
+        st.shard_tensor.append(cpu_part, -1)
+    dist.barrier(group)  # nobody gathers before every peer mapping exists
+    return st

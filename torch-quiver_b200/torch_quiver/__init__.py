@@ -327,6 +327,16 @@ class ShardTensor:
         self.shards.append(_Shard(int(item.device), ptr.value, int(item.shape[0]), _pitch_for(row_bytes),
                                   ipc_opened=True, shape=list(item.shape)))
 
+    def adopt(self, other):
+        """Move the (single) shard of another ShardTensor to the end of this one, keeping ownership of its memory
+        (used when ranks assemble a table in rank order: quiver.shard_tensor.build_from_ranks)."""
+        if len(other.shards) != 1:
+            raise RuntimeError("adopt() takes a ShardTensor holding exactly one shard")
+        sh = other.shards[0]
+        self._admit(sh.shape, other.element_size, other.dtype)
+        self.shards.append(sh)
+        other.shards.clear()
+
     # -- ShardTensor.__getitem__(indices) ---------------------------------------------------------------------------
     def _table(self, current_device):
         t = ShardTable()
