@@ -49,7 +49,11 @@ namespace
 std::mutex g_reg_mu;
 // host registrations we made: base -> (bytes). Lets qv_host_unregister undo exactly what was registered and makes
 // repeated registration of the same tensor idempotent.
-std::unordered_map<void *, size_t> g_registered;
+struct Registration {
+    size_t bytes;
+    int refs;
+};
+std::unordered_map<void *, Registration> g_registered;
 }  // namespace
 
 extern "C" {
@@ -166,18 +170,21 @@ int qv_host_register(int device, void *host_ptr, size_t bytes, void **dev_ptr)
     if (bytes == 0) bytes = 1;
     DeviceGuard g(device);
     std::lock_guard<std::mutex> lk(g_reg_mu);
-    // One registration for the whole range: the reference splits it into 1e9-byte pieces whose boundaries are
-    // not page aligned (quiver.cu.hpp:19-25); a single cudaHostRegister has no such seams.
-    cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
-    if (e == cudaErrorHostMemoryAlreadyRegistered) {
-        cudaGetLastError();
-        e = cudaSuccess;
-    } else if (e == cudaSuccess) {
-        g_registered[host_ptr] = bytes;
-    }
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(QV_ERR_CUDA, "cudaHostRegister(%p, %zu): %s", host_ptr, bytes, cudaGetErrorString(e));
+    auto it = g_registered.find(host_ptr);
+    if (it != g_registered.end() && it->second.bytes >= bytes) {
+        it->second.refs++;  // same tensor shared by several tables: one registration, counted
+    } else {
+        // One registration for the whole range: the reference splits it into 1e9-byte pieces whose boundaries are
+        // not page aligned (quiver.cu.hpp:19-25); a single cudaHostRegister has no such seams.
+        cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+        if (e == cudaErrorHostMemoryAlreadyRegistered) {
+            cudaGetLastError();  // pinned by someone else (e.g. torch pin_memory): usable, not ours to undo
+        } else if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(QV_ERR_CUDA, "cudaHostRegister(%p, %zu): %s", host_ptr, bytes, cudaGetErrorString(e));
+        } else {
+            g_registered[host_ptr] = Registration{bytes, 1};
+        }
     }
     QV_CUDA(cudaHostGetDevicePointer(dev_ptr, host_ptr, 0));
     return QV_OK;
@@ -189,6 +196,7 @@ int qv_host_unregister(void *host_ptr)
     std::lock_guard<std::mutex> lk(g_reg_mu);
     auto it = g_registered.find(host_ptr);
     if (it == g_registered.end()) return QV_OK;  // not ours (or already undone)
+    if (--it->second.refs > 0) return QV_OK;
     g_registered.erase(it);
     QV_CUDA(cudaHostUnregister(host_ptr));
     return QV_OK;

@@ -192,8 +192,10 @@ class Feature(object):
         self.ipc_handle_ = ipc_handle
 
     def share_ipc(self):
-        self.cpu_part.share_memory_()
         stores = self.device_tensor_list if self.cache_policy == "device_replicate" else self.clique_tensor_list
+        for st in stores.values():  # the cold tier moves to shared memory; keep its zero-copy registration valid
+            st.shard_tensor.move_host_tier_to_shared_memory()
+        self.cpu_part.share_memory_()
         gpu_ipc_handle_dict = {key: st.share_ipc()[0] for key, st in stores.items()}
         cpu_part = self.cpu_part if self.cpu_part.numel() > 0 else None
         return gpu_ipc_handle_dict, cpu_part, self.device_list, self.device_cache_size, self.cache_policy, self.csr_topo

@@ -233,11 +233,12 @@ class ShardTensorItem:
 
 
 class _Shard:
-    __slots__ = ("device", "ptr", "rows", "pitch", "owned", "ipc_opened", "host_tensor", "shape")
+    __slots__ = ("device", "ptr", "rows", "pitch", "owned", "ipc_opened", "host_tensor", "host_base", "shape")
 
     def __init__(self, device, ptr, rows, pitch, owned=False, ipc_opened=False, host_tensor=None, shape=None):
         self.device, self.ptr, self.rows, self.pitch = device, ptr, rows, pitch
         self.owned, self.ipc_opened, self.host_tensor, self.shape = owned, ipc_opened, host_tensor, shape
+        self.host_base = host_tensor.data_ptr() if (host_tensor is not None and ptr) else 0  # what we registered
 
 
 class ShardTensor:
@@ -266,6 +267,9 @@ class ShardTensor:
                     lib.qv_free(sh.device, c_void_p(sh.ptr))
                 elif sh.ipc_opened and sh.ptr:
                     lib.qv_ipc_close_handle(sh.device, c_void_p(sh.ptr))
+                elif sh.host_base:
+                    # a registration that outlives its memory poisons later cudaMemcpy calls on reused addresses
+                    lib.qv_host_unregister(c_void_p(sh.host_base))
             except Exception:  # interpreter shutdown
                 pass
         shards.clear()
@@ -421,4 +425,26 @@ class ShardTensor:
         return items
 
     def unregister(self, cpu_tensor):
+        """ShardTensor.unregister(cpu_tensor) -- quiver_feature.cu:354-360."""
         check(lib.qv_host_unregister(_ptr(cpu_tensor)))
+        for sh in self.shards:
+            if sh.host_base == cpu_tensor.data_ptr():
+                sh.host_base = 0
+
+    def move_host_tier_to_shared_memory(self):
+        """`tensor.share_memory_()` on the zero-copy host tier WITHOUT leaving a dangling registration: the storage
+        moves to a new mapping, so the old range is unregistered first and the new one registered after.  (The
+        reference calls share_memory_() on a registered tensor, feature.py:383-384, which leaves the parent process
+        reading freed memory.)"""
+        for sh in self.shards:
+            if sh.host_tensor is None or sh.host_tensor.is_shared() or sh.host_tensor.numel() == 0:
+                continue
+            if sh.host_base:
+                check(lib.qv_host_unregister(c_void_p(sh.host_base)))
+                sh.host_base, sh.ptr = 0, 0
+            sh.host_tensor.share_memory_()
+            alias = c_void_p()
+            check(lib.qv_host_register(self.device_, _ptr(sh.host_tensor),
+                                       sh.host_tensor.numel() * sh.host_tensor.element_size(), byref(alias)))
+            sh.ptr, sh.host_base = alias.value, sh.host_tensor.data_ptr()
+        self._table_cache = None
