@@ -121,7 +121,8 @@ typedef struct qv_shard_table {
  * `out` is a dense [n, row_bytes] buffer on the current device.  Rows whose index is < 0 or >= total rows (or
  * whose shard is not accessible) are written as zeros -- the reference leaves them uninitialised
  * (shard_tensor.cu.hpp:49).  Pure byte copy: 0 ULP for any element type.  Asynchronous on `stream`.
- * `variant`: 0 = auto, 1 = SIMT vector gather, 2 = TMA bulk-copy pipeline (needs row_bytes % 16 == 0). */
+ * `variant`: 0 = auto, 1 = batched SIMT row gather, 2 = TMA bulk-copy pipeline (needs row_bytes % 16 == 0),
+ *            3 = flat chunked SIMT gather (kept for comparison). */
 QV_API int qv_gather(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
               int64_t row_bytes, void *out, int variant, qv_stream_t stream);
 

@@ -38,7 +38,7 @@ def gather():
         st.append(x, 0)
         idxs = [torch.randint(0, rows, (n, ), device="cuda") for _ in range(4)]
         rb = d * x.element_size()
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             if variant == 2 and rb % 16:
                 continue
             st.gather_variant = variant

@@ -18,7 +18,7 @@ def _np(t):
     return t.view(torch.int16).numpy() if t.dtype in (torch.float16, torch.bfloat16) else t.numpy()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("d", [100, 128, 256, 602, 768, 1, 3, 17, 600])
 def test_single_shard_matches_oracle_and_indexing(oracle, d, dtype, variant):
@@ -40,7 +40,7 @@ def test_single_shard_matches_oracle_and_indexing(oracle, d, dtype, variant):
     assert st.stride(0) == d and st.device() == 0 and st.device_count() == 1
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("d,dtype", [(128, torch.float32), (602, torch.float32), (600, torch.float16), (100, torch.float32)])
 def test_tiers_hbm_shards_plus_pinned_host(oracle, d, dtype, variant):
     import torch_quiver as qv
@@ -64,7 +64,7 @@ def test_tiers_hbm_shards_plus_pinned_host(oracle, d, dtype, variant):
     assert np.array_equal(_np(got.cpu()), oracle.gather(parts, idx))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_invalid_ids_give_zero_rows_and_feature_order_is_folded(oracle, variant):
     import torch_quiver as qv
     n, d = 5000, 64

@@ -141,6 +141,128 @@ __global__ void __launch_bounds__(kGatherThreads)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Variant 1 (default): batched row gather.  A warp owns 32 consecutive output rows.
+//   phase 1  lane r resolves row r: coalesced 8-byte index load, optional feature_order hop, shard lookup -> source
+//            pointer (32 independent dependent-load chains in flight per warp);
+//   phase 2  the rows are copied kUnroll at a time: the source pointer of a row is broadcast with shuffles, lanes move
+//            16-byte chunks (all loads of the kUnroll rows are issued before the first store).  Rows shorter than a
+//            warp-width of chunks are packed kGroup lanes per row so no lane idles.
+// kLoad/kStore: 16/16 when everything is 16-byte aligned; 16/8 when rows are 8-byte multiples but sources are padded
+// to 16 (e.g. 602 fp32 = 2408 B rows: 16-byte loads, split stores); otherwise kLoad == kStore in {8,4,2,1}.
+// About 10 instructions per row-chunk-iteration instead of ~190 for the flat variant (no division, one shard search
+// per row instead of per chunk).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kBatchUnroll = 4;
+
+template <int kLoad, int kStore, int kGroup>
+__global__ void __launch_bounds__(256)
+    gather_batch_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
+                        const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, char *__restrict__ out)
+{
+    using L = Chunk<kLoad>;
+    constexpr int kRowsPerIter = 32 / kGroup;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % kGroup, grp = lane / kGroup;
+    const int64_t n_rows_total = t.row_begin[t.n_shards];
+    const uint32_t cpr = (row_bytes + kLoad - 1) / kLoad;  // load-chunks per row (last one may be half used: 16/8 mode)
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t base = warp * 32;
+    if (base >= n) return;
+
+    const char *my_src = nullptr;
+    if (base + lane < n) my_src = row_source(t, logical_row(indices, feature_order, n_rows_total, base + lane));
+    const int rows_here = static_cast<int>(min(static_cast<int64_t>(32), n - base));
+    char *out_base = out + base * row_bytes;
+
+    for (int rr = 0; rr < rows_here; rr += kRowsPerIter * kBatchUnroll) {
+        const char *src[kBatchUnroll];
+        int row[kBatchUnroll];
+#pragma unroll
+        for (int u = 0; u < kBatchUnroll; u++) {
+            row[u] = rr + u * kRowsPerIter + grp;
+            const unsigned long long p = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_src), row[u] & 31);
+            src[u] = reinterpret_cast<const char *>(p);
+        }
+        for (uint32_t c = sub; c < cpr; c += kGroup) {
+            typename L::T v[kBatchUnroll];
+#pragma unroll
+            for (int u = 0; u < kBatchUnroll; u++)
+                v[u] = (row[u] < rows_here && src[u]) ? L::load(src[u] + static_cast<size_t>(c) * kLoad) : L::zero();
+#pragma unroll
+            for (int u = 0; u < kBatchUnroll; u++) {
+                if (row[u] < rows_here) {
+                    char *dst = out_base + static_cast<size_t>(row[u]) * row_bytes + static_cast<size_t>(c) * kLoad;
+                    if constexpr (kLoad == kStore) {
+                        L::store(dst, v[u]);
+                    } else {  // 16-byte load, two 8-byte stores; the row's last chunk may hold only 8 valid bytes
+                        static_assert(kLoad == 16 && kStore == 8, "only the 16/8 split is implemented");
+                        st_stream_v2(dst, make_int2(v[u].x, v[u].y));
+                        if (c * 16u + 8u < row_bytes) st_stream_v2(dst + 8, make_int2(v[u].z, v[u].w));
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Same batching, but the 32 rows of a warp are walked as ONE flat run of chunks (chunk f -> row f / cpr, column
+// f % cpr, exact 32-bit multiply-high division), so rows whose chunk count is not a multiple of the group width keep
+// every lane busy: 400-byte rows (25 chunks) use 32/32 lanes instead of 25/32.
+template <int kLoad, int kStore>
+__global__ void __launch_bounds__(256, 5)
+    gather_batch_flat_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
+                             const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, uint32_t cpr,
+                             uint32_t inv, char *__restrict__ out)
+{
+    using L = Chunk<kLoad>;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_rows_total = t.row_begin[t.n_shards];
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t base = warp * 32;
+    if (base >= n) return;
+
+    const char *my_src = nullptr;
+    if (base + lane < n) my_src = row_source(t, logical_row(indices, feature_order, n_rows_total, base + lane));
+    const uint32_t rows_here = static_cast<uint32_t>(min(static_cast<int64_t>(32), n - base));
+    const uint32_t total = rows_here * cpr;
+    char *out_base = out + base * row_bytes;
+
+    for (uint32_t f0 = 0; f0 < total; f0 += 32 * kBatchUnroll) {
+        const char *src[kBatchUnroll];
+        uint32_t off[kBatchUnroll];  // byte offset of the chunk inside the warp's output run
+        uint32_t col[kBatchUnroll];
+        bool live[kBatchUnroll];
+#pragma unroll
+        for (int u = 0; u < kBatchUnroll; u++) {
+            const uint32_t f = f0 + u * 32 + lane;
+            live[u] = f < total;
+            const uint32_t row = live[u] ? __umulhi(f, inv) : 0;  // exact: f * cpr < 2^32 (host-checked)
+            col[u] = f - row * cpr;
+            off[u] = row * row_bytes + col[u] * kLoad;
+            const unsigned long long p = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_src), row);
+            src[u] = reinterpret_cast<const char *>(p);
+        }
+        typename L::T v[kBatchUnroll];
+#pragma unroll
+        for (int u = 0; u < kBatchUnroll; u++)
+            v[u] = (live[u] && src[u]) ? L::load(src[u] + static_cast<size_t>(col[u]) * kLoad) : L::zero();
+#pragma unroll
+        for (int u = 0; u < kBatchUnroll; u++) {
+            if (live[u]) {
+                char *dst = out_base + off[u];
+                if constexpr (kLoad == kStore) {
+                    L::store(dst, v[u]);
+                } else {
+                    static_assert(kLoad == 16 && kStore == 8, "only the 16/8 split is implemented");
+                    st_stream_v2(dst, make_int2(v[u].x, v[u].y));
+                    if (col[u] * 16u + 8u < row_bytes) st_stream_v2(dst + 8, make_int2(v[u].z, v[u].w));
+                }
+            }
+        }
+    }
+}
+
 // Fallback for rows too long for the 32-bit trick: one warp per row, 64-bit addressing.
 template <int kBytes>
 __global__ void __launch_bounds__(256)
@@ -305,6 +427,43 @@ inline int pick_chunk(int64_t row_bytes, const qv_shard_table *tab, const void *
     return 1;
 }
 
+template <int kLoad, int kStore>
+int launch_batch(const GatherParams &p, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                 int64_t row_bytes, char *out, cudaStream_t st)
+{
+    const int64_t cpr = (row_bytes + kLoad - 1) / kLoad;
+    const int64_t warps = (n + 31) / 32;
+    const int64_t blocks = (warps + 7) / 8;
+    QV_REQUIRE(blocks < (int64_t(1) << 31) && row_bytes < (int64_t(1) << 31), "qv_gather: request too large");
+    const unsigned g = static_cast<unsigned>(blocks);
+    const uint32_t rb = static_cast<uint32_t>(row_bytes);
+    if ((cpr & (cpr - 1)) != 0 && (cpr % 32) != 0 && cpr <= 8192 && row_bytes * 32 < (int64_t(1) << 31)) {
+        // rows that would leave lanes idle in the grouped kernel: flat walk (32 * cpr * cpr < 2^32 holds)
+        const uint32_t inv = static_cast<uint32_t>((uint64_t(1) << 32) / static_cast<uint64_t>(cpr)) + 1u;
+        gather_batch_flat_kernel<kLoad, kStore><<<g, 256, 0, st>>>(p, indices, feature_order, n, rb,
+                                                                    static_cast<uint32_t>(cpr), inv, out);
+        QV_CHECK_LAUNCH("gather_batch_flat_kernel");
+        return QV_OK;
+    }
+#define QV_LAUNCH_GROUP(G)                                                                                     \
+    gather_batch_kernel<kLoad, kStore, G><<<g, 256, 0, st>>>(p, indices, feature_order, n, rb, out)
+    if (cpr > 16)
+        QV_LAUNCH_GROUP(32);
+    else if (cpr > 8)
+        QV_LAUNCH_GROUP(16);
+    else if (cpr > 4)
+        QV_LAUNCH_GROUP(8);
+    else if (cpr > 2)
+        QV_LAUNCH_GROUP(4);
+    else if (cpr > 1)
+        QV_LAUNCH_GROUP(2);
+    else
+        QV_LAUNCH_GROUP(1);
+#undef QV_LAUNCH_GROUP
+    QV_CHECK_LAUNCH("gather_batch_kernel");
+    return QV_OK;
+}
+
 template <int kBytes>
 int launch_simt(const GatherParams &p, const int64_t *indices, const int64_t *feature_order, int64_t n,
                 int64_t row_bytes, char *out, int n_sm, cudaStream_t st)
@@ -383,6 +542,27 @@ extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, co
                                                    rows_per_stage, o);
         QV_CHECK_LAUNCH("gather_tma_kernel");
         return QV_OK;
+    }
+    if (variant != 3) {
+        // can sources be read 16 bytes at a time even though rows are only 8-byte multiples?
+        bool src16 = true;
+        for (int s = 0; s < table->n_shards; s++)
+            if (table->row_begin[s + 1] > table->row_begin[s] &&
+                ((reinterpret_cast<uintptr_t>(table->ptr[s]) | static_cast<uintptr_t>(table->pitch[s])) & 15))
+                src16 = false;
+        switch (chunk) {
+        case 16:
+            return launch_batch<16, 16>(p, indices, feature_order, n, row_bytes, o, st);
+        case 8:
+            if (src16) return launch_batch<16, 8>(p, indices, feature_order, n, row_bytes, o, st);
+            return launch_batch<8, 8>(p, indices, feature_order, n, row_bytes, o, st);
+        case 4:
+            return launch_batch<4, 4>(p, indices, feature_order, n, row_bytes, o, st);
+        case 2:
+            return launch_batch<2, 2>(p, indices, feature_order, n, row_bytes, o, st);
+        default:
+            return launch_batch<1, 1>(p, indices, feature_order, n, row_bytes, o, st);
+        }
     }
     switch (chunk) {
     case 16:

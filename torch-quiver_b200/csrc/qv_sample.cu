@@ -20,6 +20,7 @@
 //   * reservoir slots live in shared memory (32-bit), row metadata for a warp's 16 rows is fetched in one wave;
 //   * int64 ids and 64-bit sizes throughout (the reference truncates to int in several places).
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 #include "qv_common.cuh"
@@ -225,11 +226,163 @@ constexpr int kSampleTile = 64;
 constexpr int kRowsPerWarp = kSampleTile / kSampleWarps;  // 16
 constexpr int kSmemSlots = 1024;                          // per warp; larger fan-outs use the output row as slots
 
-template <bool kSlotsInSmem>
+// Exact `curand() % m < k` without the XU pipe.  The first profile of this kernel showed the XU pipe 93% busy: nvcc
+// lowers a 32-bit `%` by a runtime divisor to I2F + MUFU.RCP + F2I (quarter-rate units).  The divisors a lane meets are
+// m = k+1+lane+32j -- a sequence that does not depend on the row -- so the sampler keeps one table
+// recip[m] = floor((2^64-1)/m)+1 for every m up to the graph's maximum degree (built once per graph) and uses the
+// 64-bit "fastmod" identity (Lemire, Kaser, Kurz 2019): with low = recip[m]*r mod 2^64, r mod m == mulhi64(low, m),
+// exact for all 32-bit r, m.  `low < recip[m]*k` is a conservative filter for r mod m < k (never a false negative), so
+// the exact remainder is only formed for the rare candidates.  Divisors beyond the table fall back to `%`.
+struct RecipTable {
+    const unsigned long long *recip;  // [n]; recip[0] = recip[1] = 0
+    unsigned int n;
+};
+
+__device__ __forceinline__ void reservoir_hit(unsigned long long M, uint32_t r, uint32_t m, uint32_t kk, uint32_t idx,
+                                              uint32_t *slots)
+{
+    const unsigned long long low = M * r;
+    if (low < M * kk) {
+        const uint32_t num = static_cast<uint32_t>(__umul64hi(low, m));
+        if (num < kk) atomicMax(&slots[num], idx);
+    }
+}
+
+// The reservoir loop of one row for one lane: idx = k+lane, k+lane+32, ... < deg; one XORWOW draw per idx, in order.
+// The reciprocals are streamed through a 4-deep register ring (loads for draws j+4..j+7 are issued before draws
+// j..j+3 are evaluated): a hub row walks the table linearly, and without the ring every iteration of a lone warp
+// would stall on an L2 round trip (measured: 3x slower than the XU-bound `%` loop).
+template <bool kFast>
+__device__ __forceinline__ void reservoir_fill(Xorwow &rng, const RecipTable &rt, uint32_t kk, uint32_t udeg, int lane,
+                                               uint32_t *slots)
+{
+    uint32_t idx = kk + lane;
+    if (kFast) {
+        const uint32_t fast_end = rt.n > 1 ? min(udeg, rt.n - 1) : 0;  // idx + 1 < rt.n
+        if (idx < fast_end) {
+            const unsigned long long *tab = rt.recip + 1;  // tab[idx] = recip[idx + 1]
+            unsigned long long M0 = tab[idx];
+            unsigned long long M1 = idx + 32 < fast_end ? tab[idx + 32] : 0;
+            unsigned long long M2 = idx + 64 < fast_end ? tab[idx + 64] : 0;
+            unsigned long long M3 = idx + 96 < fast_end ? tab[idx + 96] : 0;
+            while (true) {
+                const uint32_t nb = idx + 128;
+                const unsigned long long N0 = nb < fast_end ? tab[nb] : 0;
+                const unsigned long long N1 = nb + 32 < fast_end ? tab[nb + 32] : 0;
+                const unsigned long long N2 = nb + 64 < fast_end ? tab[nb + 64] : 0;
+                const unsigned long long N3 = nb + 96 < fast_end ? tab[nb + 96] : 0;
+                reservoir_hit(M0, xorwow_next(rng), idx + 1, kk, idx, slots);
+                if (idx + 32 < fast_end) reservoir_hit(M1, xorwow_next(rng), idx + 33, kk, idx + 32, slots);
+                if (idx + 64 < fast_end) reservoir_hit(M2, xorwow_next(rng), idx + 65, kk, idx + 64, slots);
+                if (idx + 96 < fast_end) reservoir_hit(M3, xorwow_next(rng), idx + 97, kk, idx + 96, slots);
+                if (nb >= fast_end) break;
+                idx = nb;
+                M0 = N0;
+                M1 = N1;
+                M2 = N2;
+                M3 = N3;
+            }
+            // first index of this lane's progression at or beyond fast_end
+            const uint32_t first = kk + lane;
+            idx = first + ((fast_end - first + 31) / 32) * 32;
+        }
+    }
+    for (; idx < udeg; idx += 32) {  // divisors beyond the table (or kFast == false): plain modulo
+        const uint32_t num = xorwow_next(rng) % (idx + 1);
+        if (num < kk) atomicMax(&slots[num], idx);
+    }
+}
+
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                     static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Fan-outs up to 32 (every GraphSAGE configuration in BASELINE.json): one sampled id per lane per row.
+// The ids of a row are fetched with cp.async into a per-warp staging tile as soon as the row's reservoir is final and
+// are only waited for after the warp's last row, so the random 8-byte reads (HBM or zero-copy host memory) overlap the
+// generator loops of the following rows instead of serialising one memory latency per row.
+template <bool kFast>
+__global__ void __launch_bounds__(kSampleWarps * 32)
+    sample_rows_small_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
+                             const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int k,
+                             const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
+                             const RecipTable rt, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
+                             const int64_t *__restrict__ d_row_off)
+{
+    __shared__ uint32_t slots_sh[kSampleWarps][32];
+    __shared__ int64_t stage_sh[kSampleWarps][kRowsPerWarp][32];
+    const int64_t S = dev_size(S_arg, d_S);
+    const int64_t b = blockIdx.x;
+    if (b * kSampleTile >= S) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t kk = static_cast<uint32_t>(k);
+
+    Xorwow rng;
+    {
+        const uint32_t *p = rng_states + static_cast<size_t>(b) * kRngStateWords * kRngBlockThreads + threadIdx.x;
+        rng.d = p[0 * kRngBlockThreads];
+        rng.v0 = p[1 * kRngBlockThreads];
+        rng.v1 = p[2 * kRngBlockThreads];
+        rng.v2 = p[3 * kRngBlockThreads];
+        rng.v3 = p[4 * kRngBlockThreads];
+        rng.v4 = p[5 * kRngBlockThreads];
+    }
+    int64_t my_start = 0, my_deg = 0, my_o = 0;
+    {
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
+        if (lane < kRowsPerWarp && r < S) {
+            const int64_t node = seeds[r];
+            my_o = out_ptr[r];
+            if (node >= 0 && node < n_nodes) {
+                my_start = indptr[node];
+                my_deg = indptr[node + 1] - my_start;
+            }
+        }
+    }
+    uint32_t *slots = slots_sh[w];
+    int n_rows = 0;
+    for (int i = 0; i < kRowsPerWarp; i++) {
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
+        if (r >= S) break;
+        n_rows = i + 1;
+        const int64_t start = __shfl_sync(0xffffffffu, my_start, i);
+        const int64_t deg = __shfl_sync(0xffffffffu, my_deg, i);
+        if (deg <= k) {
+            if (lane < deg) cp_async_8(&stage_sh[w][i][lane], indices + start + lane);
+        } else {
+            slots[lane] = lane;
+            __syncwarp();
+            const uint32_t udeg = static_cast<uint32_t>(deg);
+            reservoir_fill<kFast>(rng, rt, kk, udeg, lane, slots);
+            __syncwarp();
+            if (lane < k) cp_async_8(&stage_sh[w][i][lane], indices + start + slots[lane]);
+            __syncwarp();
+        }
+    }
+    cp_async_wait_all();
+    const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
+    for (int i = 0; i < n_rows; i++) {
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
+        const int64_t deg = __shfl_sync(0xffffffffu, my_deg, i);
+        const int64_t o = __shfl_sync(0xffffffffu, my_o, i);
+        const int64_t cnt = deg <= k ? deg : k;
+        if (lane < cnt) {
+            out[o + lane] = stage_sh[w][i][lane];
+            if (row_out) row_out[row_off + o + lane] = r;
+        }
+    }
+}
+
+template <bool kSlotsInSmem, bool kFast = true>
 __global__ void __launch_bounds__(kSampleWarps * 32)
     sample_rows_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
                        const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k_arg,
-                       const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
+                       const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states, const RecipTable rt,
                        int64_t *__restrict__ out, int64_t *__restrict__ row_out, const int64_t *__restrict__ d_row_off)
 {
     __shared__ uint32_t slots_sh[kSlotsInSmem ? kSampleWarps * kSmemSlots : 1];
@@ -281,10 +434,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             const uint32_t kk = static_cast<uint32_t>(k);
             for (uint32_t j = lane; j < kk; j += 32) slots[j] = j;
             __syncwarp();
-            for (int64_t idx = k + lane; idx < deg; idx += 32) {
-                const uint32_t num = xorwow_next(rng) % static_cast<uint32_t>(idx + 1);
-                if (num < kk) atomicMax(&slots[num], static_cast<uint32_t>(idx));
-            }
+            const uint32_t udeg = static_cast<uint32_t>(deg);
+            reservoir_fill<kFast>(rng, rt, kk, udeg, lane, slots);
             __syncwarp();
             for (uint32_t j = lane; j < kk; j += 32) out[o + j] = indices[start + slots[j]];
             __syncwarp();
@@ -434,6 +585,24 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+__global__ void __launch_bounds__(256)
+    max_degree_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, unsigned long long *__restrict__ result)
+{
+    long long best = 0;
+    for (int64_t v = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; v < n_nodes;
+         v += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        best = max(best, static_cast<long long>(indptr[v + 1] - indptr[v]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(result, static_cast<unsigned long long>(best));
+}
+
+__global__ void __launch_bounds__(256) recip_table_kernel(unsigned long long *__restrict__ recip, unsigned int n)
+{
+    for (unsigned int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x)
+        recip[m] = m < 2 ? 0ull : (0xFFFFFFFFFFFFFFFFull / m + 1ull);
+}
+
 __global__ void set_meta_kernel(int64_t *meta, int idx, int64_t value) { meta[idx] = value; }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -529,6 +698,9 @@ struct qv_sampler {
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+    Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
+    unsigned int recip_n = 0;
+    int64_t max_degree = 0;
 };
 
 namespace
@@ -620,12 +792,26 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     QV_TRY(rng_states_for(s, rand_seed, S_arg, d_S, S_bound, st, &states));
     const int64_t blocks = (S_bound + kSampleTile - 1) / kSampleTile;
     QV_REQUIRE(blocks < (int64_t(1) << 31), "sample: too many seeds (%lld)", (long long)S_bound);
-    if (k < 0 || k <= kSmemSlots) {
+    const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n};
+    static const int impl = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;  // tuning switch
+    if (k >= 0 && k <= 32 && !(impl & 1)) {
+        if (impl & 2)
+            sample_rows_small_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+                s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
+                row_out, d_row_off);
+        else
+            sample_rows_small_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+                s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
+                row_out, d_row_off);
+    } else if (impl & 2) {
+        sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
+    } else if (k < 0 || k <= kSmemSlots) {
         sample_rows_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, out, row_out, d_row_off);
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
     } else {
         sample_rows_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, out, row_out, d_row_off);
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
     }
     QV_CHECK_LAUNCH("sample_rows_kernel");
     return QV_OK;
@@ -695,6 +881,36 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
         delete s;
         return fail(QV_ERR_CUDA, "qv_sampler_create: %s", cudaGetErrorString(e));
     }
+    // largest degree of the graph -> size of the divisor table used by the reservoir loop (one pass over indptr)
+    {
+        unsigned long long *d_max = reinterpret_cast<unsigned long long *>(s->d_meta);
+        if (n_nodes > 0) {
+            max_degree_kernel<<<grid_for(n_nodes, 256, s->n_sm, 8), 256>>>(indptr, n_nodes, d_max);
+            count_launch();
+        }
+        unsigned long long h_max = 0;
+        e = cudaMemcpy(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemset(s->d_meta, 0, sizeof(int64_t));
+        if (e == cudaSuccess) {
+            s->max_degree = static_cast<int64_t>(h_max);
+            const unsigned long long want = std::min<unsigned long long>(h_max + 2, 1ull << 24);
+            int rc = s->recip.ensure(static_cast<size_t>(want) * sizeof(unsigned long long));
+            if (rc != QV_OK) {
+                qv_sampler_destroy(s);
+                return rc;
+            }
+            s->recip_n = static_cast<unsigned int>(want);
+            recip_table_kernel<<<grid_for(static_cast<int64_t>(want), 256, s->n_sm, 8), 256>>>(
+                static_cast<unsigned long long *>(s->recip.ptr), s->recip_n);
+            count_launch();
+            e = cudaDeviceSynchronize();
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            qv_sampler_destroy(s);
+            return fail(QV_ERR_CUDA, "qv_sampler_create: %s", cudaGetErrorString(e));
+        }
+    }
     *out = s;
     return QV_OK;
 }
@@ -712,6 +928,7 @@ int qv_sampler_destroy(qv_sampler *s)
     s->rng_mats.release();
     s->rng_cache.release();
     s->rng_tmp.release();
+    s->recip.release();
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
     delete s;
