@@ -7,14 +7,18 @@ OUT="$HERE/../torch_quiver/libquiver_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 mkdir -p "$HERE/build"
 objs=()
+pids=()
 for f in qv_runtime qv_xorwow qv_sample qv_gather; do
   src="$HERE/$f.cu"; obj="$HERE/build/$f.o"
   if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/qv_common.cuh" -nt "$obj" || "$HERE/qv_xorwow.cuh" -nt "$obj" || "$ROOT/include/quiver_b200.h" -nt "$obj" ]]; then
     "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden \
       -I"$ROOT/include" "$@" -c "$src" -o "$obj" &
+    pids+=($!)
   fi
   objs+=("$obj")
 done
-wait
+for pid in "${pids[@]:-}"; do
+  if [[ -n "$pid" ]]; then wait "$pid" || { echo "build failed" >&2; rm -f "$HERE"/build/*.o; exit 1; }; fi
+done
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC "${objs[@]}" -o "$OUT" -lpthread -ldl -lrt
 echo "built $OUT"

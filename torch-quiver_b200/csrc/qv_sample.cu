@@ -302,11 +302,22 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Fan-outs up to 32 (every GraphSAGE configuration in BASELINE.json): one sampled id per lane per row.
-// The ids of a row are fetched with cp.async into a per-warp staging tile as soon as the row's reservoir is final and
-// are only waited for after the warp's last row, so the random 8-byte reads (HBM or zero-copy host memory) overlap the
-// generator loops of the following rows instead of serialising one memory latency per row.
-template <bool kFast>
+// Fan-outs up to 32 (every GraphSAGE configuration in BASELINE.json).
+//
+// Profiling the first two versions of this kernel on the products-shaped bench batch (170 k rows in the last hop) showed
+// that the reservoir draws themselves are ~1/4 of the issued instructions (1.8 warp-iterations per row on average); the
+// rest was per-row overhead -- shuffles, warp syncs, a dependent memory latency and a 5/32-lane-wide gather per row --
+// plus one SM grinding through a 29 k-degree hub row at ~250 cycles per draw long after the others had finished.
+// What parity fixes is only this: lane l owns ONE generator stream that serves the lane's draws of row 0, then row 1, ...
+// and the number of draws it makes in a row, ceil((deg - k - l) / 32), is known up front.  Hence:
+//   * the 16 reservoirs of a warp's rows are all live in shared memory, so the row loop needs NO warp synchronisation:
+//     a lane just walks its stream row after row, results meet through shared-memory atomicMax (commutative);
+//   * long runs inside one row (hubs) go 8 draws per trip with the fastmod reciprocals of the NEXT trip already in
+//     flight and all 8 generator outputs produced before the first test, so a lone warp is not serialised on one
+//     divide-and-branch latency per draw; short rows use the plain `%` (nothing to look up);
+//   * the ids to emit (verbatim rows and chosen positions alike) are handled as ONE flat list of <= 16*k entries per
+//     warp -- 32 lanes wide instead of k lanes wide -- fetched with cp.async into a staging tile (verbatim rows before
+//     the generator loop even starts) and written out after a single wait.
 __global__ void __launch_bounds__(kSampleWarps * 32)
     sample_rows_small_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
                              const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int k,
@@ -314,8 +325,13 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
                              const RecipTable rt, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
                              const int64_t *__restrict__ d_row_off)
 {
-    __shared__ uint32_t slots_sh[kSampleWarps][32];
-    __shared__ int64_t stage_sh[kSampleWarps][kRowsPerWarp][32];
+    __shared__ uint32_t slots_sh[kSampleWarps][kRowsPerWarp][32];
+    __shared__ int64_t stage_sh[kSampleWarps][kRowsPerWarp * 32];
+    __shared__ int64_t start_sh[kSampleWarps][kRowsPerWarp];
+    __shared__ int64_t o_sh[kSampleWarps][kRowsPerWarp];
+    __shared__ uint32_t deg_sh[kSampleWarps][kRowsPerWarp];
+    __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
+    __shared__ uint8_t rowof_sh[kSampleWarps][kRowsPerWarp * 32];  // entry -> row
     const int64_t S = dev_size(S_arg, d_S);
     const int64_t b = blockIdx.x;
     if (b * kSampleTile >= S) return;
@@ -332,8 +348,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
         rng.v3 = p[4 * kRngBlockThreads];
         rng.v4 = p[5 * kRngBlockThreads];
     }
-    int64_t my_start = 0, my_deg = 0, my_o = 0;
+    // lane i < 16 owns the metadata of row i; one inclusive warp scan lays the rows' entries out back to back
+    uint32_t n_entries;
     {
+        int64_t my_start = 0, my_deg = 0, my_o = 0;
         const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
         if (lane < kRowsPerWarp && r < S) {
             const int64_t node = seeds[r];
@@ -343,38 +361,98 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
                 my_deg = indptr[node + 1] - my_start;
             }
         }
-    }
-    uint32_t *slots = slots_sh[w];
-    int n_rows = 0;
-    for (int i = 0; i < kRowsPerWarp; i++) {
-        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
-        if (r >= S) break;
-        n_rows = i + 1;
-        const int64_t start = __shfl_sync(0xffffffffu, my_start, i);
-        const int64_t deg = __shfl_sync(0xffffffffu, my_deg, i);
-        if (deg <= k) {
-            if (lane < deg) cp_async_8(&stage_sh[w][i][lane], indices + start + lane);
-        } else {
-            slots[lane] = lane;
-            __syncwarp();
-            const uint32_t udeg = static_cast<uint32_t>(deg);
-            reservoir_fill<kFast>(rng, rt, kk, udeg, lane, slots);
-            __syncwarp();
-            if (lane < k) cp_async_8(&stage_sh[w][i][lane], indices + start + slots[lane]);
-            __syncwarp();
+        const uint32_t cnt = static_cast<uint32_t>(my_deg <= k ? my_deg : k);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int off = 1; off < kRowsPerWarp; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
         }
+        n_entries = __shfl_sync(0xffffffffu, incl, kRowsPerWarp - 1);
+        if (lane < kRowsPerWarp) {
+            deg_sh[w][lane] = static_cast<uint32_t>(min(my_deg, static_cast<int64_t>(0xffffffffu)));
+            start_sh[w][lane] = my_start;
+            o_sh[w][lane] = my_o;
+            pre_sh[w][lane] = static_cast<uint16_t>(incl - cnt);
+            for (uint32_t j = 0; j < cnt; j++) rowof_sh[w][incl - cnt + j] = static_cast<uint8_t>(lane);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerWarp; i++) slots_sh[w][i][lane] = lane;
+    __syncwarp();
+
+    // verbatim rows: their ids can start travelling now
+    for (uint32_t e = lane; e < n_entries; e += 32) {
+        const int i = rowof_sh[w][e];
+        if (deg_sh[w][i] <= kk) cp_async_8(&stage_sh[w][e], indices + start_sh[w][i] + (e - pre_sh[w][i]));
+    }
+
+    // this lane's generator stream, row after row, no synchronisation
+    {
+        const uint32_t first = kk + lane;
+        const unsigned long long *tab = rt.recip + 1;  // tab[idx] = recip[idx + 1]
+        const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
+        for (int i = 0; i < kRowsPerWarp; i++) {
+            const uint32_t d = deg_sh[w][i];
+            if (d <= first) continue;
+            uint32_t rem = (d - first + 31) >> 5, idx = first;
+            uint32_t *srow = slots_sh[w][i];
+            if (rem >= 8 && idx + 512 < tab_n) {
+                unsigned long long M[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) M[u] = tab[idx + 32 * u];
+                while (true) {
+                    unsigned long long N[8];
+                    const bool more = rem >= 16 && idx + 768 < tab_n;
+                    if (more) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) N[u] = tab[idx + 256 + 32 * u];
+                    }
+                    uint32_t r[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) r[u] = xorwow_next(rng);
+                    bool cand = false;
+                    unsigned long long low[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        low[u] = M[u] * r[u];
+                        cand |= low[u] < M[u] * kk;
+                    }
+                    if (cand) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const uint32_t num = static_cast<uint32_t>(__umul64hi(low[u], idx + 32 * u + 1));
+                            if (num < kk) atomicMax(&srow[num], idx + 32 * u);
+                        }
+                    }
+                    idx += 256;
+                    rem -= 8;
+                    if (!more) break;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) M[u] = N[u];
+                }
+            }
+            for (; rem > 0; rem--, idx += 32) {
+                const uint32_t num = xorwow_next(rng) % (idx + 1);
+                if (num < kk) atomicMax(&srow[num], idx);
+            }
+        }
+    }
+    __syncwarp();
+
+    // sampled rows: fetch the chosen positions; then one wait and one coalesced write-out of the whole list
+    for (uint32_t e = lane; e < n_entries; e += 32) {
+        const int i = rowof_sh[w][e];
+        if (deg_sh[w][i] > kk)
+            cp_async_8(&stage_sh[w][e], indices + start_sh[w][i] + slots_sh[w][i][e - pre_sh[w][i]]);
     }
     cp_async_wait_all();
     const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
-    for (int i = 0; i < n_rows; i++) {
-        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
-        const int64_t deg = __shfl_sync(0xffffffffu, my_deg, i);
-        const int64_t o = __shfl_sync(0xffffffffu, my_o, i);
-        const int64_t cnt = deg <= k ? deg : k;
-        if (lane < cnt) {
-            out[o + lane] = stage_sh[w][i][lane];
-            if (row_out) row_out[row_off + o + lane] = r;
-        }
+    for (uint32_t e = lane; e < n_entries; e += 32) {
+        const int i = rowof_sh[w][e];
+        const int64_t dst = o_sh[w][i] + (e - pre_sh[w][i]);
+        out[dst] = stage_sh[w][e];
+        if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
     }
 }
 
@@ -795,14 +873,9 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n};
     static const int impl = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;  // tuning switch
     if (k >= 0 && k <= 32 && !(impl & 1)) {
-        if (impl & 2)
-            sample_rows_small_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-                s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-                row_out, d_row_off);
-        else
-            sample_rows_small_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-                s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-                row_out, d_row_off);
+        sample_rows_small_kernel<<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
+            row_out, d_row_off);
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
             s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
