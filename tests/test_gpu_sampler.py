@@ -140,9 +140,11 @@ def test_reindex_bit_exact(oracle, golden_dir):
         assert torch.equal(col.cpu(), torch.from_numpy(ocol)), S
 
 
+@pytest.mark.parametrize("reindex", ["map", "hash"])
 @pytest.mark.parametrize("sizes", [[25, 10], [15, 10, 5], [3], [2, 2, 2, 2], [40, 0, 3]])
-def test_fused_khop_equals_oracle_and_per_hop(oracle, sizes):
+def test_fused_khop_equals_oracle_and_per_hop(oracle, sizes, reindex, monkeypatch):
     import quiver
+    monkeypatch.setenv("QV_KHOP_REINDEX", reindex)  # direct node map (default) vs per-hop hash table
     indptr, indices = powerlaw_csr(20000, 25.0, seed=10)
     topo = quiver.CSRTopo(indptr=indptr, indices=indices)
     sampler = quiver.pyg.GraphSageSampler(topo, sizes, device=0, mode="GPU")
@@ -164,6 +166,31 @@ def test_fused_khop_equals_oracle_and_per_hop(oracle, sizes):
     assert torch.equal(n_id2, n_id)
     for a, b in zip(adjs, adjs2):
         assert torch.equal(a.edge_index, b.edge_index) and a.size.tolist() == b.size.tolist()
+
+
+def test_fused_khop_repeated_calls_and_bad_seeds(oracle):
+    """The node map persists across calls (reset after every sample); invalid seeds reroute the call to the hash path."""
+    import quiver
+    indptr, indices = powerlaw_csr(8000, 15.0, seed=14)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [6, 4], device=0, mode="GPU")
+    rng = np.random.default_rng(0)
+    for it in range(4):
+        seeds = rng.permutation(8000)[:300] if it != 2 else np.concatenate([rng.integers(0, 8000, 200)] * 2)  # dups
+        n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [6, 4])
+        assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid)), it
+        for adj, (o_ei, _) in zip(adjs, o_adjs):
+            assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)), it
+    bad = torch.tensor([5, 8000, 17, -3, 42, 2**40])
+    n_id, bs, adjs = sampler.sample(bad)
+    sampler.fused = False
+    n_id2, _, adjs2 = sampler.sample(bad)
+    assert torch.equal(n_id, n_id2) and all(torch.equal(a.edge_index, b.edge_index) for a, b in zip(adjs, adjs2))
+    sampler.fused = True
+    seeds = rng.permutation(8000)[:300]  # the map must be clean again after the rerouted call
+    n_id, _, _ = sampler.sample(torch.from_numpy(seeds))
+    assert torch.equal(n_id.cpu(), torch.from_numpy(oracle.khop(indptr, indices, seeds, [6, 4])[0]))
 
 
 def test_full_neighbourhood_hop_falls_back(oracle):

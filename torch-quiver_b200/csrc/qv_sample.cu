@@ -80,7 +80,7 @@ __device__ __forceinline__ long long warp_sum_i64(long long v)
 // Returns the exclusive prefix of this thread's `thread_sum` over the whole grid; `tile` is the ticketed tile index.
 // Must be called by all kScanThreads threads.  The last tile stores the grand total to *d_total.
 __device__ __forceinline__ long long chained_scan(long long thread_sum, ScanState st, int tile, int n_tiles,
-                                                  int64_t *d_total)
+                                                  int64_t *d_total, long long total_base = 0)
 {
     __shared__ long long warp_tot[kScanThreads / 32];
     __shared__ long long tile_excl_sh;
@@ -136,7 +136,7 @@ __device__ __forceinline__ long long chained_scan(long long thread_sum, ScanStat
         }
         if (lane == 0) {
             tile_excl_sh = excl;
-            if (tile == n_tiles - 1 && d_total) *d_total = excl + block_agg;
+            if (tile == n_tiles - 1 && d_total) *d_total = total_base + excl + block_agg;
         }
     }
     __syncthreads();
@@ -663,6 +663,99 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused k-hop reindex over a DIRECT node map (one int32 per graph node, kept across the hops of a sample() call).
+// The frontier of hop h+1 is the frontier of hop h plus the not-yet-seen sampled nodes in first-occurrence order, with
+// unchanged local ids for the old ones -- so the hash table rebuilt from scratch every hop (reference:
+// quiver_sample.cu:202-255, one cudaMalloc+cudaMemset per call) is unnecessary inside a k-hop sample:
+//   map[v] = kMapUnseen             not in the frontier
+//   map[v] = i >= 0                 candidate: smallest item index of v among this hop's items (atomicMin)
+//   map[v] = local | 0x80000000     in the frontier with that local id (negative as int32: atomicMin never touches it)
+// Per hop only the E sampled ids are processed (not S+E), with 4-byte accesses and no probing; the map is reset for
+// the frontier's nodes after the last hop.  Ids outside [0, n_nodes) raise a flag and the call is redone on the
+// hash path (they can only come from invalid user seeds or a corrupt CSR).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMapUnseen = 0x7F7F7F7F;
+
+__global__ void __launch_bounds__(256)
+    map_insert_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
+                      const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
+                      int64_t n_nodes, int64_t *__restrict__ d_err)
+{
+    const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
+    const int64_t n = P + E;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t key = i < P ? prefix[i] : outputs[i - P];
+        if (static_cast<uint64_t>(key) >= static_cast<uint64_t>(n_nodes)) {
+            *d_err = 1;
+            continue;
+        }
+        atomicMin(&map[key], static_cast<int>(i));
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    map_scan_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
+                    const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
+                    int64_t n_nodes, const int64_t *__restrict__ d_F_prev, int64_t *__restrict__ frontier,
+                    int64_t *__restrict__ d_F, ScanState st, int n_tiles)
+{
+    const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
+    const int64_t n = P + E;
+    const long long F_prev = d_F_prev ? *d_F_prev : 0;
+    const int tile = take_ticket(st);
+    const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
+    long long key[kScanItems];
+    bool first[kScanItems];
+    long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        const int64_t i = base + j;
+        first[j] = false;
+        key[j] = 0;
+        if (i < n) {
+            key[j] = i < P ? prefix[i] : outputs[i - P];
+            if (static_cast<uint64_t>(key[j]) < static_cast<uint64_t>(n_nodes))
+                first[j] = map[key[j]] == static_cast<int>(i);
+        }
+        sum += first[j] ? 1 : 0;
+    }
+    long long local = F_prev + chained_scan(sum, st, tile, n_tiles, d_F, F_prev);
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        if (first[j]) {
+            frontier[local] = key[j];
+            map[key[j]] = static_cast<int>(static_cast<unsigned int>(local) | 0x80000000u);
+            local++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    map_emit_kernel(const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, const int *__restrict__ map,
+                    int64_t n_nodes, int64_t *__restrict__ col_idx)
+{
+    const int64_t E = *d_E;
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t key = outputs[e];
+        col_idx[e] = static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes) ? (map[key] & 0x7FFFFFFF) : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    map_reset_kernel(const int64_t *__restrict__ frontier, const int64_t *__restrict__ d_F, int *__restrict__ map,
+                     int64_t n_nodes)
+{
+    const int64_t F = *d_F;
+    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < F;
+         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t key = frontier[j];
+        if (static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes)) map[key] = kMapUnseen;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     max_degree_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, unsigned long long *__restrict__ result)
 {
@@ -765,6 +858,7 @@ struct qv_sampler {
 
     int64_t *d_meta = nullptr;  // kMetaWords device scalars
     int64_t *h_meta = nullptr;  // pinned mirror
+    cudaEvent_t meta_ready = nullptr;
     Buffer scan;                // two scan-state regions
     size_t scan_region_words = 0;
     Buffer table;  // Slot[2^table_log2]
@@ -776,6 +870,8 @@ struct qv_sampler {
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+    Buffer node_map;  // int32 per graph node: direct first-occurrence map of the fused k-hop path
+    bool map_ready = false, map_dirty = false;
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
     unsigned int recip_n = 0;
     int64_t max_degree = 0;
@@ -948,6 +1044,7 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&s->d_meta), kMetaWords * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMemset(s->d_meta, 0, kMetaWords * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_meta), kMetaWords * sizeof(int64_t), 0);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->meta_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (s->d_meta) cudaFree(s->d_meta);
@@ -1002,8 +1099,10 @@ int qv_sampler_destroy(qv_sampler *s)
     s->rng_cache.release();
     s->rng_tmp.release();
     s->recip.release();
+    s->node_map.release();
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
+    if (s->meta_ready) cudaEventDestroy(s->meta_ready);
     delete s;
     return QV_OK;
 }
@@ -1089,6 +1188,86 @@ int qv_khop_bounds(int64_t S, const int64_t *sizes, int n_hops, int64_t *bound_n
     return QV_OK;
 }
 
+namespace
+{
+constexpr int kMetaErr = kMetaStride * QV_MAX_HOPS + 3;  // a free device scalar: "id outside [0, n_nodes) seen"
+
+// One attempt of the fused k-hop.  use_map: direct node map (default) or the per-hop hash table.
+int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+             int64_t *n_id, int64_t *const *edge_buf, const int64_t *bn, const int64_t *be, bool use_map, cudaStream_t st,
+             bool *id_error)
+{
+    int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
+    int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
+    int *map = static_cast<int *>(s->node_map.ptr);
+    int64_t *d_err = s->d_meta + kMetaErr;
+    *id_error = false;
+    if (use_map) {
+        if (!s->map_ready || s->map_dirty) {
+            QV_CUDA(cudaMemsetAsync(map, 0x7F, static_cast<size_t>(std::max<int64_t>(s->n_nodes, 1)) * sizeof(int), st));
+            s->map_ready = true;
+        }
+        s->map_dirty = true;
+    }
+    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaS, S);
+    QV_CHECK_LAUNCH("set_meta_kernel");
+    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaErr, 0);
+    QV_CHECK_LAUNCH("set_meta_kernel");
+    for (int h = 0; h < n_hops; h++) {
+        int64_t *m = s->d_meta + kMetaStride * h;
+        const int64_t *d_S = m + kMetaS;
+        int64_t *d_E = m + kMetaE;
+        int64_t *d_F = m + kMetaF;
+        const int64_t *hop_seeds = h == 0 ? seeds : n_id;
+        QV_TRY(zero_scan_regions(s, bn[h], bn[h] + be[h], st));
+        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st));
+        // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
+        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st));
+        if (!use_map) {
+            QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
+                                  nullptr, 1, st));
+        } else {
+            // hop 0 also enters the seeds (they become local ids 0..S-1, duplicates merged); later hops only add
+            const int64_t *prefix = h == 0 ? seeds : nullptr;
+            const int64_t items = (h == 0 ? bn[0] : 0) + be[h];
+            if (items > 0) {
+                map_insert_kernel<<<grid_for(items, 256, s->n_sm), 256, 0, st>>>(prefix, 0, d_S, nbr, d_E, map,
+                                                                                  s->n_nodes, d_err);
+                QV_CHECK_LAUNCH("map_insert_kernel");
+            }
+            const int n_tiles = tiles_for(items);
+            map_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
+                                                               h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 1),
+                                                               n_tiles);
+            QV_CHECK_LAUNCH("map_scan_kernel");
+            if (be[h] > 0) {
+                map_emit_kernel<<<grid_for(be[h], 256, s->n_sm), 256, 0, st>>>(nbr, d_E, map, s->n_nodes, edge_buf[h]);
+                QV_CHECK_LAUNCH("map_emit_kernel");
+            }
+        }
+        // the next hop's seed count is this hop's frontier size
+        QV_CUDA(cudaMemcpyAsync(m + kMetaStride + kMetaS, d_F, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    // the size read-back is complete once this event fires; the map reset enqueued after it overlaps the host's work
+    QV_CUDA(cudaEventRecord(s->meta_ready, st));
+    if (use_map) {
+        map_reset_kernel<<<grid_for(bn[n_hops], 256, s->n_sm), 256, 0, st>>>(
+            n_id, s->d_meta + kMetaStride * (n_hops - 1) + kMetaF, map, s->n_nodes);
+        QV_CHECK_LAUNCH("map_reset_kernel");
+    }
+    QV_CUDA(cudaEventSynchronize(s->meta_ready));
+    if (use_map) {
+        if (s->h_meta[kMetaErr] != 0) {
+            *id_error = true;  // map state is unspecified: force a clean one next time
+            return QV_OK;
+        }
+        s->map_dirty = false;
+    }
+    return QV_OK;
+}
+}  // namespace
+
 int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
             int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream)
 {
@@ -1099,6 +1278,7 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
     for (int h = 0; h < n_hops; h++) out_edges[h] = 0;
     if (S == 0) return QV_OK;
     QV_REQUIRE(seeds && n_id && edge_buf, "qv_khop: NULL array");
+    for (int h = 0; h < n_hops; h++) QV_REQUIRE(edge_buf[h] != nullptr || be[h] == 0, "qv_khop: edge_buf[%d] is NULL", h);
     DeviceGuard g(s->device);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -1107,33 +1287,24 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
         max_nodes = std::max(max_nodes, bn[h]);
         max_edges = std::max(max_edges, be[h]);
     }
+    const char *env = getenv("QV_KHOP_REINDEX");  // "hash" forces the per-hop hash table (tests / A-B)
+    bool use_map = !(env && env[0] == 'h') && s->n_nodes > 0 && s->n_nodes < (int64_t(1) << 31) &&
+                   bn[n_hops] < int64_t(kMapUnseen);
     QV_TRY(ensure_scan(s, bn[n_hops]));
-    QV_TRY(ensure_table(s, bn[n_hops]));
     QV_TRY(s->out_ptr.ensure(static_cast<size_t>(max_nodes) * sizeof(int64_t)));
     QV_TRY(s->nbr.ensure(static_cast<size_t>(std::max<int64_t>(max_edges, 1)) * sizeof(int64_t)));
-    int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
-    int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
-
-    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaS, S);
-    QV_CHECK_LAUNCH("set_meta_kernel");
-    for (int h = 0; h < n_hops; h++) {
-        QV_REQUIRE(edge_buf[h] != nullptr || be[h] == 0, "qv_khop: edge_buf[%d] is NULL", h);
-        int64_t *m = s->d_meta + kMetaStride * h;
-        const int64_t *d_S = m + kMetaS;
-        int64_t *d_E = m + kMetaE;
-        int64_t *d_F = m + kMetaF;
-        const int64_t *hop_seeds = h == 0 ? seeds : n_id;
-        QV_TRY(zero_scan_regions(s, bn[h], bn[h] + be[h], st));
-        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st));
-        // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
-        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st));
-        QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr, nullptr,
-                              1, st));
-        // the next hop's seed count is this hop's frontier size
-        QV_CUDA(cudaMemcpyAsync(m + kMetaStride + kMetaS, d_F, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (use_map && !s->node_map.ptr) {
+        if (s->node_map.ensure(static_cast<size_t>(s->n_nodes) * sizeof(int)) != QV_OK) use_map = false;  // no room
+        s->map_ready = false;
     }
-    QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    QV_CUDA(cudaStreamSynchronize(st));
+    if (!use_map) QV_TRY(ensure_table(s, bn[n_hops]));
+
+    bool id_error = false;
+    QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, use_map, st, &id_error));
+    if (id_error) {
+        QV_TRY(ensure_table(s, bn[n_hops]));
+        QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, false, st, &id_error));
+    }
     for (int h = 0; h < n_hops; h++) {
         out_edges[h] = s->h_meta[kMetaStride * h + kMetaE];
         out_nodes[h + 1] = s->h_meta[kMetaStride * h + kMetaF];
