@@ -177,3 +177,35 @@ def test_shards_are_freed():
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 100 * 2**20  # the reference never frees shards (no destructor): SURVEY.md 8(b)
+
+
+def test_reddit_scale_sample_then_tiered_gather():
+    """BASELINE config 0 shape (Reddit: 232,965 nodes, ~114 M edges, fan-out [25,10], 602-d fp32 = 2408-byte rows that are
+    only 8-byte multiples) with the reference's bench placement "20 % of the rows cached on the GPU, the rest in host
+    memory" (docs/Introduction_en.md:95-97): sampled n_id -> feature[n_id] must equal x[n_id] bit for bit, through the
+    degree-ordered hot/cold split."""
+    import quiver
+    N, D = 232_965, 602
+    g = torch.Generator(device="cuda").manual_seed(3)
+    raw = (1.0 - torch.rand(N, generator=g, device="cuda", dtype=torch.float64)).pow(-0.5)
+    deg = (raw * (491.5 / raw.mean())).floor().long().clamp_(max=N - 1)
+    indptr = torch.zeros(N + 1, dtype=torch.long, device="cuda")
+    indptr[1:] = deg.cumsum(0)
+    indices = torch.randint(0, N, (int(indptr[-1]), ), generator=g, device="cuda")
+    topo = quiver.CSRTopo(indptr=indptr.cpu(), indices=indices.cpu())
+    del indices
+    x = torch.rand(N, D)
+    budget = int(0.2 * N) * D * 4
+    feature = quiver.Feature(rank=0, device_list=[0], device_cache_size=budget, cache_policy="device_replicate",
+                             csr_topo=topo)
+    feature.from_cpu_tensor(x)
+    st = feature.device_tensor_list[0].shard_tensor
+    assert st.device_count() == 2 and st.size(0) == N  # hot HBM shard + zero-copy host tier
+    sampler = quiver.pyg.GraphSageSampler(topo, [25, 10], device=0, mode="GPU")
+    seeds = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:1024]
+    n_id, bs, adjs = sampler.sample(seeds)
+    assert bs == 1024 and torch.equal(n_id[:bs].cpu(), seeds)
+    assert sum(a.edge_index.shape[1] for a in adjs) > 200_000
+    rows = feature[n_id]
+    assert rows.shape == (n_id.numel(), D)
+    assert torch.equal(rows.cpu(), x[n_id.cpu()])

@@ -166,8 +166,8 @@ class Feature(object):
 
     # ---- the hot call ---------------------------------------------------------------------------------------------
     def __getitem__(self, node_idx: torch.Tensor):
-        self.lazy_init_from_ipc_handle()
-        node_idx = node_idx.to(self.rank)
+        if self.ipc_handle_ is not None:
+            self.lazy_init_from_ipc_handle()
         return self._my_store().gather(node_idx, self.feature_order)
 
     def size(self, dim: int):

@@ -26,6 +26,9 @@ class _FakeDevice(object):
     pass
 
 
+_EMPTY_E_ID = torch.tensor([])
+
+
 class GraphSageSampler:
     r"""Behaves like PyG's `NeighborSampler`: `sample(seeds)` returns `(n_id, batch_size, adjs)` with `adjs` ordered
     outermost hop first, `adj.edge_index[0]` indexing into `n_id` (sources) and `edge_index[1]` into the hop's targets.
@@ -92,8 +95,10 @@ class GraphSageSampler:
             except qv.Unsupported:
                 pass
             else:
-                adjs = [Adj(edge_index, torch.tensor([]), torch.LongTensor([n_src, n_dst]))
-                        for edge_index, n_src, n_dst in hops]
+                # e_id is always empty in the reference (sage_sampler.py:143); one shared empty tensor, one host tensor
+                # for all the (n_src, n_dst) pairs
+                sizes = torch.tensor([[n_src, n_dst] for _, n_src, n_dst in hops], dtype=torch.long)
+                adjs = [Adj(hop[0], _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
                 return n_id, batch_size, adjs[::-1]
         adjs = []
         for size in self.sizes:

@@ -40,6 +40,7 @@ class ShardTensor:
         self.topo = None
         self.current_clique = None
         self.cpu_tensor = None
+        self._other_cache = None
 
     def init_topo(self):
         if self.current_clique is not None:
@@ -95,11 +96,20 @@ class ShardTensor:
     def __getitem__(self, nodes):
         return self.gather(nodes)
 
+    def _other_clique_devices(self):
+        """GPUs that hold rows but sit outside this device's P2P clique (cached until the placement changes)."""
+        key = len(self.shard_tensor_config.tensor_offset_device)
+        if self._other_cache is None or self._other_cache[0] != key:
+            self.init_topo()
+            other = [d for c, devs in self.topo.p2pClique2Device.items() if c != self.current_clique for d in devs
+                     if self.shard_tensor_config.tensor_offset_device.get(d) is not None]
+            self._other_cache = (key, other)
+        return self._other_cache[1]
+
     def gather(self, nodes, feature_order=None):
-        self.init_topo()
-        nodes = nodes.to(self.current_device)
-        other = [d for c, devs in self.topo.p2pClique2Device.items() if c != self.current_clique for d in devs
-                 if self.shard_tensor_config.tensor_offset_device.get(d) is not None]
+        if not nodes.is_cuda or nodes.device.index != self.current_device:
+            nodes = nodes.to(self.current_device)
+        other = self._other_clique_devices()
         if not other:
             return self.shard_tensor.gather(nodes, feature_order)
         if feature_order is not None:

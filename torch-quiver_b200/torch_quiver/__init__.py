@@ -78,6 +78,7 @@ class Quiver:
         self.device = int(device)
         self.rand_seed = 0  # the reference hard-codes 0 (quiver.cu.hpp:392); change it to draw a different sample
         self._keep = []  # tensors whose memory the C object borrows
+        self._khop_plans = {}  # (S, sizes) -> cached bounds / ctypes scratch of sample_khop
         self._registered = None
         self._handle = c_void_p()
         if indptr.dim() != 1 or indices.dim() != 1:
@@ -169,25 +170,37 @@ class Quiver:
         per-hop calls)."""
         v = _check_long_cuda(seeds, "seeds", self.device)
         n_hops = len(sizes)
-        if not 1 <= n_hops <= QV_MAX_HOPS:
-            raise Unsupported(_lib.QV_ERR_UNSUPPORTED, f"{n_hops} hops")
         S = v.numel()
-        sz = (c_int64 * n_hops)(*[int(s) for s in sizes])
-        bn = (c_int64 * (n_hops + 1))()
-        be = (c_int64 * n_hops)()
-        check(lib.qv_khop_bounds(S, sz, n_hops, bn, be))
-        n_id = torch.empty(max(bn[n_hops], 1), dtype=torch.int64, device=v.device)
-        bufs = [torch.empty(max(2 * be[h], 1), dtype=torch.int64, device=v.device) for h in range(n_hops)]
-        buf_ptrs = (c_void_p * n_hops)(*[b.data_ptr() for b in bufs])
-        out_nodes = (c_int64 * (n_hops + 1))()
-        out_edges = (c_int64 * n_hops)()
-        check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), _ptr(n_id), buf_ptrs, out_nodes,
+        key = (S, tuple(int(x) for x in sizes))
+        plan = self._khop_plans.get(key)
+        if plan is None:
+            if not 1 <= n_hops <= QV_MAX_HOPS:
+                raise Unsupported(_lib.QV_ERR_UNSUPPORTED, f"{n_hops} hops")
+            sz = (c_int64 * n_hops)(*key[1])
+            bn = (c_int64 * (n_hops + 1))()
+            be = (c_int64 * n_hops)()
+            check(lib.qv_khop_bounds(S, sz, n_hops, bn, be))
+            # one allocation per call: [n_id | edge_buf[0] | edge_buf[1] | ...], every piece 16-byte aligned
+            offs, total = [], (max(bn[n_hops], 1) + 1) // 2 * 2
+            for h in range(n_hops):
+                offs.append(total)
+                total += max(2 * be[h], 2)
+            plan = (sz, bn[n_hops], offs, total, (c_void_p * n_hops)(), (c_int64 * (n_hops + 1))(), (c_int64 * n_hops)())
+            if len(self._khop_plans) > 64:
+                self._khop_plans.clear()
+            self._khop_plans[key] = plan
+        sz, n_id_cap, offs, total, buf_ptrs, out_nodes, out_edges = plan
+        arena = torch.empty(total, dtype=torch.int64, device=v.device)
+        base = arena.data_ptr()
+        for h in range(n_hops):
+            buf_ptrs[h] = base + 8 * offs[h]
+        check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs, out_nodes,
                           out_edges, _stream(self.device)))
         hops = []
         for h in range(n_hops):
             E = out_edges[h]
-            hops.append((bufs[h][:2 * E].view(2, E), out_nodes[h + 1], out_nodes[h]))
-        return n_id[:out_nodes[n_hops]], hops
+            hops.append((arena[offs[h]:offs[h] + 2 * E].view(2, E), out_nodes[h + 1], out_nodes[h]))
+        return arena[:out_nodes[n_hops]], hops
 
 
 def device_quiver_from_csr_array(indptr, indices, edge_ids=None, device=0, cuda=False):
@@ -375,9 +388,13 @@ class ShardTensor:
         if cache is None or cache[0] != (key, len(self.shards)):
             self._table_cache = ((key, len(self.shards)), self._table(current))
         table = self._table_cache[1]
-        with torch.cuda.device(current):
+        if torch.cuda.current_device() == current:
             check(lib.qv_gather(byref(table), _ptr(idx), order_ptr, n, self._row_bytes(), _ptr(out),
                                 int(self.gather_variant), _stream(current)))
+        else:
+            with torch.cuda.device(current):
+                check(lib.qv_gather(byref(table), _ptr(idx), order_ptr, n, self._row_bytes(), _ptr(out),
+                                    int(self.gather_variant), _stream(current)))
         return out
 
     def __getitem__(self, indices):
