@@ -157,7 +157,8 @@ __device__ __forceinline__ int take_ticket(ScanState st)
 __global__ void __launch_bounds__(kScanThreads)
     count_scan_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, const int64_t *__restrict__ seeds,
                       int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k, int64_t *__restrict__ counts,
-                      int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles)
+                      int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles,
+                      const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t *__restrict__ d_err)
 {
     const int64_t S = dev_size(S_arg, d_S);
     const int tile = take_ticket(st);
@@ -169,10 +170,18 @@ __global__ void __launch_bounds__(kScanThreads)
         const int64_t i = base + j;
         long long v = 0;
         if (i < S) {
-            const int64_t node = seeds[i];
-            if (node >= 0 && node < n_nodes) {
-                const int64_t deg = indptr[node + 1] - indptr[node];
+            if (cached_deg) {  // hop >= 1 of a fused k-hop: the frontier's degrees were recorded when its nodes joined
+                const int64_t deg = cached_deg[i];
                 v = (k >= 0 && deg > k) ? k : deg;
+            } else {
+                const int64_t node = seeds[i];
+                if (node >= 0 && node < n_nodes) {
+                    const int64_t deg = indptr[node + 1] - indptr[node];
+                    v = (k >= 0 && deg > k) ? k : deg;
+                    if (node_map) atomicMin(&node_map[node], static_cast<int>(i));  // hop 0: seeds enter the node map
+                } else if (node_map) {
+                    *d_err = 1;
+                }
             }
         }
         c[j] = v;
@@ -323,7 +332,9 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
                              const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int k,
                              const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
                              const RecipTable rt, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
-                             const int64_t *__restrict__ d_row_off)
+                             const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
+                             const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t item_base_arg,
+                             const int64_t *__restrict__ d_item_base, int64_t *__restrict__ d_err)
 {
     __shared__ uint32_t slots_sh[kSampleWarps][kRowsPerWarp][32];
     __shared__ int64_t stage_sh[kSampleWarps][kRowsPerWarp * 32];
@@ -354,11 +365,16 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
         int64_t my_start = 0, my_deg = 0, my_o = 0;
         const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
         if (lane < kRowsPerWarp && r < S) {
-            const int64_t node = seeds[r];
             my_o = out_ptr[r];
-            if (node >= 0 && node < n_nodes) {
-                my_start = indptr[node];
-                my_deg = indptr[node + 1] - my_start;
+            if (cached_deg) {
+                my_start = cached_start[r];
+                my_deg = cached_deg[r];
+            } else {
+                const int64_t node = seeds[r];
+                if (node >= 0 && node < n_nodes) {
+                    my_start = indptr[node];
+                    my_deg = indptr[node + 1] - my_start;
+                }
             }
         }
         const uint32_t cnt = static_cast<uint32_t>(my_deg <= k ? my_deg : k);
@@ -448,11 +464,19 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     }
     cp_async_wait_all();
     const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
+    const int64_t item_base = node_map ? (d_item_base ? *d_item_base : item_base_arg) : 0;
     for (uint32_t e = lane; e < n_entries; e += 32) {
         const int i = rowof_sh[w][e];
         const int64_t dst = o_sh[w][i] + (e - pre_sh[w][i]);
-        out[dst] = stage_sh[w][e];
+        const int64_t id = stage_sh[w][e];
+        out[dst] = id;
         if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
+        if (node_map) {  // fused k-hop: the sampled id enters the first-occurrence map right here
+            if (static_cast<uint64_t>(id) < static_cast<uint64_t>(n_nodes))
+                atomicMin(&node_map[id], static_cast<int>(item_base + dst));
+            else
+                *d_err = 1;
+        }
     }
 }
 
@@ -699,7 +723,8 @@ __global__ void __launch_bounds__(kScanThreads)
     map_scan_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
                     const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
                     int64_t n_nodes, const int64_t *__restrict__ d_F_prev, int64_t *__restrict__ frontier,
-                    int64_t *__restrict__ d_F, ScanState st, int n_tiles)
+                    int64_t *__restrict__ d_F, ScanState st, int n_tiles, const int64_t *__restrict__ indptr,
+                    int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg)
 {
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
@@ -721,12 +746,27 @@ __global__ void __launch_bounds__(kScanThreads)
         }
         sum += first[j] ? 1 : 0;
     }
+    // a node that joins the frontier gets its CSR row located now (the loads overlap the look-back), so the next hop's
+    // count / sample kernels read (start, degree) with coalesced loads instead of two dependent random ones per seed
+    long long rs[kScanItems], rd[kScanItems];
+#pragma unroll
+    for (int j = 0; j < kScanItems; j++) {
+        rs[j] = rd[j] = 0;
+        if (first[j] && fr_deg) {
+            rs[j] = indptr[key[j]];
+            rd[j] = indptr[key[j] + 1] - rs[j];
+        }
+    }
     long long local = F_prev + chained_scan(sum, st, tile, n_tiles, d_F, F_prev);
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
         if (first[j]) {
             frontier[local] = key[j];
             map[key[j]] = static_cast<int>(static_cast<unsigned int>(local) | 0x80000000u);
+            if (fr_deg) {
+                fr_start[local] = rs[j];
+                fr_deg[local] = rd[j];
+            }
             local++;
         }
     }
@@ -870,6 +910,7 @@ struct qv_sampler {
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+    Buffer fr_meta;   // [2][bound] int64: CSR row start / degree of every frontier node (fused k-hop path)
     Buffer node_map;  // int32 per graph node: direct first-occurrence map of the fused k-hop path
     bool map_ready = false, map_dirty = false;
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
@@ -947,20 +988,31 @@ int rng_states_for(qv_sampler *s, uint64_t rand_seed, int64_t rows_arg, const in
     return QV_OK;
 }
 
+struct HopExtras {  // fused k-hop only; all null for the standalone calls
+    const int64_t *cached_start = nullptr, *cached_deg = nullptr;
+    int *node_map = nullptr;
+    int64_t item_base = 0;
+    const int64_t *d_item_base = nullptr;
+    int64_t *d_err = nullptr;
+};
+
 int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
-                      int64_t k, int64_t *counts, int64_t *out_ptr, int64_t *d_total, int region, cudaStream_t st)
+                      int64_t k, int64_t *counts, int64_t *out_ptr, int64_t *d_total, int region, cudaStream_t st,
+                      const HopExtras &x = HopExtras())
 {
     const int n_tiles = tiles_for(S_bound);
     count_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(s->indptr, s->n_nodes, seeds, S_arg, d_S, k, counts, out_ptr,
-                                                         d_total, scan_region(s, region), n_tiles);
+                                                         d_total, scan_region(s, region), n_tiles, x.cached_deg,
+                                                         x.cached_deg ? nullptr : x.node_map, x.d_err);
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
 }
 
 int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound, int64_t k,
                   uint64_t rand_seed, const int64_t *out_ptr, int64_t *out, int64_t *row_out, const int64_t *d_row_off,
-                  cudaStream_t st)
+                  cudaStream_t st, const HopExtras &x = HopExtras(), bool *fused_insert = nullptr)
 {
+    if (fused_insert) *fused_insert = false;
     if (S_bound <= 0) return QV_OK;
     const uint32_t *states = nullptr;
     QV_TRY(rng_states_for(s, rand_seed, S_arg, d_S, S_bound, st, &states));
@@ -971,7 +1023,8 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     if (k >= 0 && k <= 32 && !(impl & 1)) {
         sample_rows_small_kernel<<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
             s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-            row_out, d_row_off);
+            row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err);
+        if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
             s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
@@ -1100,6 +1153,7 @@ int qv_sampler_destroy(qv_sampler *s)
     s->rng_tmp.release();
     s->recip.release();
     s->node_map.release();
+    s->fr_meta.release();
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
     if (s->meta_ready) cudaEventDestroy(s->meta_ready);
@@ -1220,9 +1274,26 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         int64_t *d_F = m + kMetaF;
         const int64_t *hop_seeds = h == 0 ? seeds : n_id;
         QV_TRY(zero_scan_regions(s, bn[h], bn[h] + be[h], st));
-        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st));
+        HopExtras x;
+        int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start ? fr_start + bn[n_hops] : nullptr;
+        if (use_map) {
+            x.node_map = map;
+            x.d_err = d_err;
+            x.d_item_base = h == 0 ? d_S : nullptr;  // items of hop 0 are [seeds | outputs]; later hops: outputs only
+            if (h >= 1 && fr_start) {
+                x.cached_start = fr_start;
+                x.cached_deg = fr_deg;
+            }
+        }
+        bool fused_insert = false;
+        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st, x));
+        // Inserting the sampled ids into the node map from inside the sampling kernel was measured slower (+14 us on the
+        // kernel's critical blocks vs 9 us for a separate, perfectly parallel insert kernel): keep them separate.
+        HopExtras xs = x;
+        xs.node_map = nullptr;
         // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
-        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st));
+        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st, xs,
+                             &fused_insert));
         if (!use_map) {
             QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
                                   nullptr, 1, st));
@@ -1230,7 +1301,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             // hop 0 also enters the seeds (they become local ids 0..S-1, duplicates merged); later hops only add
             const int64_t *prefix = h == 0 ? seeds : nullptr;
             const int64_t items = (h == 0 ? bn[0] : 0) + be[h];
-            if (items > 0) {
+            if (items > 0 && !fused_insert) {  // fan-outs > 32 use the generic sampling kernel, which does not insert
                 map_insert_kernel<<<grid_for(items, 256, s->n_sm), 256, 0, st>>>(prefix, 0, d_S, nbr, d_E, map,
                                                                                   s->n_nodes, d_err);
                 QV_CHECK_LAUNCH("map_insert_kernel");
@@ -1238,7 +1309,8 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             const int n_tiles = tiles_for(items);
             map_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
                                                                h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 1),
-                                                               n_tiles);
+                                                               n_tiles, s->indptr, h + 1 < n_hops ? fr_start : nullptr,
+                                                               h + 1 < n_hops ? fr_deg : nullptr);
             QV_CHECK_LAUNCH("map_scan_kernel");
             if (be[h] > 0) {
                 map_emit_kernel<<<grid_for(be[h], 256, s->n_sm), 256, 0, st>>>(nbr, d_E, map, s->n_nodes, edge_buf[h]);
@@ -1298,6 +1370,11 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
         s->map_ready = false;
     }
     if (!use_map) QV_TRY(ensure_table(s, bn[n_hops]));
+    const char *env_deg = getenv("QV_KHOP_CACHE_DEG");  // "0": re-read indptr per hop instead of caching (A-B switch)
+    if (use_map && !(env_deg && env_deg[0] == '0'))
+        QV_TRY(s->fr_meta.ensure(static_cast<size_t>(2 * bn[n_hops]) * sizeof(int64_t)));
+    else
+        s->fr_meta.release();
 
     bool id_error = false;
     QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, use_map, st, &id_error));
