@@ -241,6 +241,7 @@ def run_ours(args, rank, world, local_rank):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     launches0 = _lib.launch_count()
     edges = rows = 0
+    hop_bytes = 0  # B_hop = 40*E + 40*S + 8*F algorithmic bytes per hop
     nid_keep = []
     barrier()
     ev[0].record()
@@ -250,6 +251,7 @@ def run_ours(args, rank, world, local_rank):
         res = feature[n_id]
         ev[3 * i + 2].record()
         edges += sum(a.edge_index.shape[1] for a in adjs)
+        hop_bytes += sum(40 * a.edge_index.shape[1] + 40 * int(a.size[1]) + 8 * int(a.size[0]) for a in adjs)
         rows += n_id.numel()
         nid_keep.append(n_id)
         ev[3 * i + 3].record()
@@ -303,6 +305,27 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- reduce over ranks -------------------------------------------------------------------------------------------
     stats = torch.tensor([total_ms, sample_ms, gather_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    # ---- a large-batch point (64 k seeds): the sampler where bandwidth, not launch latency, matters -------
+    big = None
+    if not args.no_large_batch:
+        gbig = torch.Generator().manual_seed(99 + rank)
+        big_batches = [torch.randperm(N_NODES, generator=gbig)[:65536].to(dev) for _ in range(3)]
+        sampler.sample(big_batches[0])
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        big_edges = big_bytes = 0
+        b0.record()
+        for bb in big_batches:
+            _, _, adjs = sampler.sample(bb)
+            big_edges += sum(a.edge_index.shape[1] for a in adjs)
+            big_bytes += sum(40 * a.edge_index.shape[1] + 40 * int(a.size[1]) + 8 * int(a.size[0]) for a in adjs)
+        b1.record()
+        barrier()
+        big_ms = b0.elapsed_time(b1)
+        big = {"seeds": 65536, "seps": big_edges / (big_ms * 1e-3), "algorithmic_GBps": big_bytes / (big_ms * 1e-3) / 1e9,
+               "frac_of_hbm_peak": big_bytes / (big_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_batch": big_ms / 3}
+        del big_batches
+
     sums = torch.tensor([edges, rows, e2e_edges, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -326,6 +349,10 @@ def run_ours(args, rank, world, local_rank):
         "feature_gather_GBps": rows_all * row_bytes / (gather_ms * 1e-3) / 1e9,
         "feature_gather_GiBps": rows_all * row_bytes / (gather_ms * 1e-3) / 2**30,
         "sample_ms_per_step": sample_ms / args.steps, "gather_ms_per_step": gather_ms / args.steps,
+        "sampler_roofline": {"bound": "hbm (nominally; at 1024 seeds the hops are launch/latency bound)",
+                             "algorithmic_bytes_per_step": hop_bytes / args.steps, "formula": "sum over hops 40E+40S+8F",
+                             "achieved": hop_bytes / (sample_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hop_bytes / (sample_ms * 1e-3) / 1e9 / hbm_peak, "large_batch": big},
         "gpu_launches": int(launches_all),
         "e2e": {"value": e2e_edges_all / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": BATCH * 8,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -375,6 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-batch", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -18,6 +18,7 @@
  * All citations are relative to /root/reference unless they name a CUDA toolkit header.
  * Plain C11, no dependencies.  Build: see oracle/Makefile.
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -340,7 +341,9 @@ QO_API void qo_cal_next(const float *last_prob, float *cur_prob, int64_t N, int 
                 skip = 1 - last_prob[u] + last_prob[u] * (udeg - k) / udeg;
             acc *= skip;
         }
-        cur_prob[row] = 1 - (1 - last_prob[row]) * acc;
+        /* `1 - (1 - p) * acc`: nvcc (default -fmad=true, which the reference build uses: setup.py:67) contracts this
+         * into a single fused multiply-add; fmaf() reproduces that rounding on the CPU */
+        cur_prob[row] = fmaf(-(1 - last_prob[row]), acc, 1.0f);
     }
 }
 

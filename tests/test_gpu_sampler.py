@@ -237,8 +237,19 @@ def test_cal_neighbor_prob(oracle):
     cur = torch.zeros(5000, device="cuda")
     q.cal_neighbor_prob(0, torch.from_numpy(p).cuda(), cur, 4)
     want = oracle.cal_next(p, 4, indptr, indices)
-    # fp32, same operation order; the only licence is FMA contraction of 1 - (1-p)*acc on the GPU (<= 1 ulp of 1.0)
-    assert np.abs(cur.cpu().numpy() - want).max() <= 1.2e-7
+    # fp32, neighbours multiplied in CSR order, the final 1 - (1-p)*acc as one FMA (as nvcc contracts it in the
+    # reference kernel): bit-identical
+    assert np.array_equal(cur.cpu().numpy(), want)
+    # two hops through the Python API (GraphSageSampler.sample_prob, sage_sampler.py:149-157)
+    import quiver
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [4, 3], device=0, mode="GPU")
+    train_idx = torch.arange(0, 5000, 7)
+    prob = sampler.sample_prob(train_idx, 5000)
+    p0 = np.zeros(5000, np.float32)
+    p0[train_idx.numpy()] = 1
+    want2 = oracle.cal_next(oracle.cal_next(p0, 4, indptr, indices), 3, indptr, indices)
+    assert np.array_equal(prob.cpu().numpy(), want2)
 
 
 def test_products_scale_properties():

@@ -144,3 +144,52 @@ def test_sampler_pickles_lazily():
     assert isinstance(s3, GraphSageSampler) and s3.csr_topo.node_count == 60
     with pytest.raises(NotImplementedError):
         GraphSageSampler(topo, [5], "cpu", "CPU")
+
+
+def _naive_partition(probs, chunk_size):
+    """Plain-Python restatement of partition.py:99-161 for checking (distinct scores, no ties)."""
+    P, n = len(probs), len(probs[0])
+    res = [[] for _ in range(P)]
+    start, rot = 0, 0
+    while start < n:
+        end = min(n, start + chunk_size * P)
+        free = set(range(start, end))
+        for r_ in range(rot, rot + P):
+            r = r_ % P
+            score = {v: P * probs[r][v] - sum(probs[q][v] for q in range(P) if q != r) for v in free}
+            take = sorted(free, key=lambda v: -score[v])[:chunk_size]
+            res[r] += take
+            free -= set(take)
+        rot += 1
+        start = end
+    return res
+
+
+def test_partition_by_access_probability(tmp_path):
+    from quiver.partition import (load_quiver_feature_partition, partition_feature_without_replication,
+                                  partition_without_replication, quiver_partition_feature, select_nodes)
+    g = torch.Generator().manual_seed(0)
+    P, n = 3, 1000
+    probs = [torch.rand(n, generator=g) for _ in range(P)]
+    parts, moved = partition_feature_without_replication(probs, 64, device="cpu")
+    allv = torch.cat(parts)
+    assert allv.numel() == n and torch.unique(allv).numel() == n  # disjoint cover
+    assert max(p.numel() for p in parts) - min(p.numel() for p in parts) <= 64
+    naive = _naive_partition([p.tolist() for p in probs], 64)
+    assert [sorted(p.tolist()) for p in parts] == [sorted(x) for x in naive]
+    # the reference's folder layout round-trips
+    book, res, cache = quiver_partition_feature(probs, str(tmp_path / "part"), cache_memory_budget="4K",
+                                                per_feature_size=16, chunk_size=64, device="cpu")
+    assert book.shape == (n, ) and all(bool((book[res[i]] == i).all()) for i in range(P))
+    assert all(c.numel() == (4096 // 16) // P for c in cache)
+    assert torch.equal(cache[1], torch.sort(probs[1], descending=True)[1][:85])
+    b2, r2, c2 = load_quiver_feature_partition(2, str(tmp_path / "part"))
+    assert torch.equal(b2, book) and torch.equal(r2, res[2]) and torch.equal(c2, cache[2])
+    with pytest.raises(FileExistsError):
+        quiver_partition_feature(probs, str(tmp_path / "part"), device="cpu")
+    # id-restricted variant + select_nodes
+    ids = torch.randperm(n, generator=g)[:300]
+    sub = partition_without_replication("cpu", probs, ids)
+    assert sorted(torch.cat(sub).tolist()) == sorted(ids.tolist())
+    s, nz = select_nodes("cpu", probs, None)
+    assert torch.allclose(s, sum(probs)) and nz.numel() == n

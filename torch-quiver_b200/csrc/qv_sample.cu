@@ -817,35 +817,48 @@ __global__ void __launch_bounds__(256) recip_table_kernel(unsigned long long *__
 __global__ void set_meta_kernel(int64_t *meta, int idx, int64_t value) { meta[idx] = value; }
 
 // ------------------------------------------------------------------------------------------------------------------
-// cal_next (cuda_random.cu.hpp:71-104): one thread per node, neighbours visited in CSR order so the fp32 product is
-// formed in the reference's order (bit-identical results).
+// cal_next (cuda_random.cu.hpp:71-104): one hop of access-probability propagation,
+//   p'[v] = 1 - (1 - p[v]) * prod_{u in N(v)} skip(u),   skip(u) = 1 - p[u] * min(1, k / deg u)   (1 when deg u = 0).
+// The reference runs one THREAD per node with a serial loop over its neighbours (three dependent random reads per
+// neighbour, a 142 k-neighbour hub in a single thread).  Here a warp owns a node: 32 neighbours' skip factors are
+// fetched in parallel, then multiplied IN CSR ORDER (each lane replays the same 32 sequential multiplies through
+// shuffles; idle lanes contribute exactly 1.0f), so the fp32 result is bit-identical to the serial loop.  Arithmetic is
+// spelled with round-to-nearest intrinsics; the final 1 - a*b is the single FMA nvcc contracts in the reference kernel.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     cal_next_kernel(const float *__restrict__ last_prob, float *__restrict__ cur_prob, int64_t N, int k,
                     const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices)
 {
-    for (int64_t row = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; row < N;
-         row += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t row = warp; row < N; row += n_warps) {
         const int64_t start = indptr[row];
         const int64_t deg = indptr[row + 1] - start;
         if (deg == 0) {
-            cur_prob[row] = 0;
+            if (lane == 0) cur_prob[row] = 0;
             continue;
         }
         float acc = 1.0f;
-        for (int64_t i = start; i < start + deg; i++) {
-            const int64_t u = indices[i];
-            const int64_t udeg = indptr[u + 1] - indptr[u];
-            float skip;
-            if (udeg == 0)
-                skip = 1;
-            else if (udeg <= k)
-                skip = 1 - last_prob[u];
-            else
-                skip = 1 - last_prob[u] + last_prob[u] * (udeg - k) / udeg;
-            acc *= skip;
+        for (int64_t base = 0; base < deg; base += 32) {
+            float skip = 1.0f;
+            if (base + lane < deg) {
+                const int64_t u = indices[start + base + lane];
+                const int64_t ustart = indptr[u];
+                const int64_t udeg = indptr[u + 1] - ustart;
+                if (udeg != 0) {
+                    const float p = last_prob[u];
+                    if (udeg <= k)
+                        skip = __fsub_rn(1.0f, p);
+                    else
+                        skip = __fadd_rn(__fsub_rn(1.0f, p),
+                                         __fdiv_rn(__fmul_rn(p, static_cast<float>(udeg - k)), static_cast<float>(udeg)));
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 32; l++) acc = __fmul_rn(acc, __shfl_sync(0xffffffffu, skip, l));
         }
-        cur_prob[row] = 1 - (1 - last_prob[row]) * acc;
+        if (lane == 0) cur_prob[row] = __fmaf_rn(-__fsub_rn(1.0f, last_prob[row]), acc, 1.0f);
     }
 }
 
@@ -1396,7 +1409,7 @@ int qv_cal_neighbor_prob(qv_sampler *s, const float *last_prob, float *cur_prob,
                (long long)s->n_nodes);
     if (n == 0) return QV_OK;
     DeviceGuard g(s->device);
-    cal_next_kernel<<<grid_for(n, 128, s->n_sm, 16), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    cal_next_kernel<<<grid_for(n * 32, 256, s->n_sm, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         last_prob, cur_prob, n, k, s->indptr, s->indices);
     QV_CHECK_LAUNCH("cal_next_kernel");
     return QV_OK;
