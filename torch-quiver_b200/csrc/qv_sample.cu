@@ -80,7 +80,8 @@ __device__ __forceinline__ long long warp_sum_i64(long long v)
 // Returns the exclusive prefix of this thread's `thread_sum` over the whole grid; `tile` is the ticketed tile index.
 // Must be called by all kScanThreads threads.  The last tile stores the grand total to *d_total.
 __device__ __forceinline__ long long chained_scan(long long thread_sum, ScanState st, int tile, int n_tiles,
-                                                  int64_t *d_total, long long total_base = 0)
+                                                  int64_t *d_total, long long total_base = 0,
+                                                  int64_t *d_total_copy = nullptr)
 {
     __shared__ long long warp_tot[kScanThreads / 32];
     __shared__ long long tile_excl_sh;
@@ -136,7 +137,10 @@ __device__ __forceinline__ long long chained_scan(long long thread_sum, ScanStat
         }
         if (lane == 0) {
             tile_excl_sh = excl;
-            if (tile == n_tiles - 1 && d_total) *d_total = total_base + excl + block_agg;
+            if (tile == n_tiles - 1) {
+                if (d_total) *d_total = total_base + excl + block_agg;
+                if (d_total_copy) *d_total_copy = total_base + excl + block_agg;
+            }
         }
     }
     __syncthreads();
@@ -627,7 +631,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(kScanThreads)
     frontier_scan_kernel(int64_t S_arg, const int64_t *__restrict__ d_S, int64_t E_arg, const int64_t *__restrict__ d_E,
                          Slot *__restrict__ table, const uint32_t *__restrict__ pos, int64_t *__restrict__ frontier,
-                         int64_t *__restrict__ d_F, ScanState st, int n_tiles)
+                         int64_t *__restrict__ d_F, ScanState st, int n_tiles, int64_t *__restrict__ d_next_S)
 {
     const int64_t n = dev_size(S_arg, d_S) + dev_size(E_arg, d_E);
     const int tile = take_ticket(st);
@@ -650,7 +654,7 @@ __global__ void __launch_bounds__(kScanThreads)
         }
         sum += first[j] ? 1 : 0;
     }
-    long long excl = chained_scan(sum, st, tile, n_tiles, d_F);
+    long long excl = chained_scan(sum, st, tile, n_tiles, d_F, 0, d_next_S);
 #pragma unroll
     for (int j = 0; j < kScanItems; j++) {
         if (first[j]) {
@@ -719,23 +723,28 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// kItems ids per thread: 4 for small hops, 16 for large ones -- the decoupled look-back advances ~32 tiles per L2 round
+// trip, so a 850 k-item hop cut into 830 tiles of 1024 spent most of its 18 us waiting on that chain; 208 tiles of
+// 4096 do not.
+template <int kItems>
 __global__ void __launch_bounds__(kScanThreads)
     map_scan_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
                     const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
                     int64_t n_nodes, const int64_t *__restrict__ d_F_prev, int64_t *__restrict__ frontier,
                     int64_t *__restrict__ d_F, ScanState st, int n_tiles, const int64_t *__restrict__ indptr,
-                    int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg)
+                    int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg,
+                    int64_t *__restrict__ d_next_S)
 {
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
     const long long F_prev = d_F_prev ? *d_F_prev : 0;
     const int tile = take_ticket(st);
-    const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
-    long long key[kScanItems];
-    bool first[kScanItems];
+    const int64_t base = static_cast<int64_t>(tile) * (kScanThreads * kItems) + threadIdx.x * kItems;
+    long long key[kItems];
+    bool first[kItems];
     long long sum = 0;
 #pragma unroll
-    for (int j = 0; j < kScanItems; j++) {
+    for (int j = 0; j < kItems; j++) {
         const int64_t i = base + j;
         first[j] = false;
         key[j] = 0;
@@ -748,18 +757,18 @@ __global__ void __launch_bounds__(kScanThreads)
     }
     // a node that joins the frontier gets its CSR row located now (the loads overlap the look-back), so the next hop's
     // count / sample kernels read (start, degree) with coalesced loads instead of two dependent random ones per seed
-    long long rs[kScanItems], rd[kScanItems];
+    long long rs[kItems], rd[kItems];
 #pragma unroll
-    for (int j = 0; j < kScanItems; j++) {
+    for (int j = 0; j < kItems; j++) {
         rs[j] = rd[j] = 0;
         if (first[j] && fr_deg) {
             rs[j] = indptr[key[j]];
             rd[j] = indptr[key[j] + 1] - rs[j];
         }
     }
-    long long local = F_prev + chained_scan(sum, st, tile, n_tiles, d_F, F_prev);
+    long long local = F_prev + chained_scan(sum, st, tile, n_tiles, d_F, F_prev, d_next_S);
 #pragma unroll
-    for (int j = 0; j < kScanItems; j++) {
+    for (int j = 0; j < kItems; j++) {
         if (first[j]) {
             frontier[local] = key[j];
             map[key[j]] = static_cast<int>(static_cast<unsigned int>(local) | 0x80000000u);
@@ -814,7 +823,11 @@ __global__ void __launch_bounds__(256) recip_table_kernel(unsigned long long *__
         recip[m] = m < 2 ? 0ull : (0xFFFFFFFFFFFFFFFFull / m + 1ull);
 }
 
-__global__ void set_meta_kernel(int64_t *meta, int idx, int64_t value) { meta[idx] = value; }
+__global__ void init_khop_meta_kernel(int64_t *meta, int64_t S, int err_idx)
+{
+    meta[kMetaS] = S;
+    meta[err_idx] = 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // cal_next (cuda_random.cu.hpp:71-104): one hop of access-probability propagation,
@@ -911,7 +924,9 @@ struct qv_sampler {
 
     int64_t *d_meta = nullptr;  // kMetaWords device scalars
     int64_t *h_meta = nullptr;  // pinned mirror
-    cudaEvent_t meta_ready = nullptr;
+    cudaEvent_t meta_ready = nullptr, reset_done = nullptr;
+    cudaStream_t side_stream = nullptr;
+    bool reset_pending = false;
     Buffer scan;                // two scan-state regions
     size_t scan_region_words = 0;
     Buffer table;  // Slot[2^table_log2]
@@ -933,13 +948,15 @@ struct qv_sampler {
 
 namespace
 {
+constexpr int kScanRegions = 2 * QV_MAX_HOPS;  // two scans per hop, every hop of a fused k-hop has its own pair
+
 int ensure_scan(qv_sampler *s, int64_t max_items)
 {
     const size_t words = static_cast<size_t>(tiles_for(max_items)) + 2;
     const size_t region = (words + 15) & ~size_t(15);
     if (region > s->scan_region_words) {
-        QV_TRY(s->scan.ensure(region * 2 * sizeof(unsigned long long)));
-        s->scan_region_words = s->scan.cap / (2 * sizeof(unsigned long long));
+        QV_TRY(s->scan.ensure(region * kScanRegions * sizeof(unsigned long long)));
+        s->scan_region_words = s->scan.cap / (kScanRegions * sizeof(unsigned long long));
     }
     return QV_OK;
 }
@@ -1062,7 +1079,7 @@ inline unsigned grid_for(int64_t items, int threads, int n_sm, int waves = 8)
 int launch_reindex(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
                    const int64_t *outputs, int64_t E_arg, const int64_t *d_E, int64_t E_bound, int64_t *frontier,
                    int64_t *d_F, int64_t *col_idx, int64_t *row_idx, const int64_t *out_ptr, int scan_which,
-                   cudaStream_t st)
+                   cudaStream_t st, int64_t *d_next_S = nullptr)
 {
     const int64_t n_bound = S_bound + E_bound;
     Slot *table = static_cast<Slot *>(s->table.ptr);
@@ -1078,7 +1095,7 @@ int launch_reindex(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int
     }
     const int n_tiles = tiles_for(n_bound);
     frontier_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(S_arg, d_S, E_arg, d_E, table, pos, frontier, d_F,
-                                                            scan_region(s, scan_which), n_tiles);
+                                                            scan_region(s, scan_which), n_tiles, d_next_S);
     QV_CHECK_LAUNCH("frontier_scan_kernel");
     if (E_bound > 0) {
         emit_edges_kernel<<<grid_for(E_bound, 256, s->n_sm), 256, 0, st>>>(S_arg, d_S, E_arg, d_E, table, pos, col_idx,
@@ -1111,6 +1128,8 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
     if (e == cudaSuccess) e = cudaMemset(s->d_meta, 0, kMetaWords * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_meta), kMetaWords * sizeof(int64_t), 0);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->meta_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->reset_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (s->d_meta) cudaFree(s->d_meta);
@@ -1170,6 +1189,8 @@ int qv_sampler_destroy(qv_sampler *s)
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
     if (s->meta_ready) cudaEventDestroy(s->meta_ready);
+    if (s->reset_done) cudaEventDestroy(s->reset_done);
+    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     delete s;
     return QV_OK;
 }
@@ -1276,17 +1297,29 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         }
         s->map_dirty = true;
     }
-    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaS, S);
-    QV_CHECK_LAUNCH("set_meta_kernel");
-    set_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, kMetaErr, 0);
-    QV_CHECK_LAUNCH("set_meta_kernel");
+    if (use_map && s->reset_pending) {  // the previous call's map reset ran on the side stream
+        QV_CUDA(cudaStreamWaitEvent(st, s->reset_done, 0));
+        s->reset_pending = false;
+    }
+    init_khop_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, S, kMetaErr);
+    QV_CHECK_LAUNCH("init_khop_meta_kernel");
+    // one memset clears the scan descriptors of every hop (each hop owns regions 2h and 2h+1)
+    if (s->scan_region_words * 2 * n_hops <= (size_t(1) << 20)) {
+        QV_CUDA(cudaMemsetAsync(s->scan.ptr, 0, s->scan_region_words * 2 * n_hops * sizeof(unsigned long long), st));
+    } else {
+        for (int h = 0; h < n_hops; h++) {
+            QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h).words, 0, (tiles_for(bn[h]) + 2) * sizeof(unsigned long long), st));
+            QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h + 1).words, 0,
+                                    (tiles_for(bn[h] + be[h]) + 2) * sizeof(unsigned long long), st));
+        }
+    }
     for (int h = 0; h < n_hops; h++) {
         int64_t *m = s->d_meta + kMetaStride * h;
         const int64_t *d_S = m + kMetaS;
         int64_t *d_E = m + kMetaE;
         int64_t *d_F = m + kMetaF;
         const int64_t *hop_seeds = h == 0 ? seeds : n_id;
-        QV_TRY(zero_scan_regions(s, bn[h], bn[h] + be[h], st));
+        int64_t *d_next_S = m + kMetaStride + kMetaS;  // the next hop's seed count is this hop's frontier size
         HopExtras x;
         int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start ? fr_start + bn[n_hops] : nullptr;
         if (use_map) {
@@ -1299,7 +1332,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             }
         }
         bool fused_insert = false;
-        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 0, st, x));
+        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
         // Inserting the sampled ids into the node map from inside the sampling kernel was measured slower (+14 us on the
         // kernel's critical blocks vs 9 us for a separate, perfectly parallel insert kernel): keep them separate.
         HopExtras xs = x;
@@ -1309,7 +1342,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                              &fused_insert));
         if (!use_map) {
             QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
-                                  nullptr, 1, st));
+                                  nullptr, 2 * h + 1, st, d_next_S));
         } else {
             // hop 0 also enters the seeds (they become local ids 0..S-1, duplicates merged); later hops only add
             const int64_t *prefix = h == 0 ? seeds : nullptr;
@@ -1319,27 +1352,39 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                                                                                   s->n_nodes, d_err);
                 QV_CHECK_LAUNCH("map_insert_kernel");
             }
-            const int n_tiles = tiles_for(items);
-            map_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
-                                                               h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 1),
-                                                               n_tiles, s->indptr, h + 1 < n_hops ? fr_start : nullptr,
-                                                               h + 1 < n_hops ? fr_deg : nullptr);
+            int64_t *fs = h + 1 < n_hops ? fr_start : nullptr, *fd = h + 1 < n_hops ? fr_deg : nullptr;
+            if (items > (int64_t(4) << 20)) {  // below that, more (smaller) tiles hide the random-load latency better
+                const int n_tiles = static_cast<int>((items + kScanThreads * 16 - 1) / (kScanThreads * 16));
+                map_scan_kernel<16><<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
+                                                                       h == 0 ? nullptr : d_S, n_id, d_F,
+                                                                       scan_region(s, 2 * h + 1), n_tiles, s->indptr, fs,
+                                                                       fd, d_next_S);
+            } else {
+                const int n_tiles = tiles_for(items);
+                map_scan_kernel<4><<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
+                                                                      h == 0 ? nullptr : d_S, n_id, d_F,
+                                                                      scan_region(s, 2 * h + 1), n_tiles, s->indptr, fs, fd,
+                                                                      d_next_S);
+            }
             QV_CHECK_LAUNCH("map_scan_kernel");
             if (be[h] > 0) {
                 map_emit_kernel<<<grid_for(be[h], 256, s->n_sm), 256, 0, st>>>(nbr, d_E, map, s->n_nodes, edge_buf[h]);
                 QV_CHECK_LAUNCH("map_emit_kernel");
             }
         }
-        // the next hop's seed count is this hop's frontier size
-        QV_CUDA(cudaMemcpyAsync(m + kMetaStride + kMetaS, d_F, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     }
     QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    // the size read-back is complete once this event fires; the map reset enqueued after it overlaps the host's work
+    // the size read-back is complete once this event fires
     QV_CUDA(cudaEventRecord(s->meta_ready, st));
     if (use_map) {
-        map_reset_kernel<<<grid_for(bn[n_hops], 256, s->n_sm), 256, 0, st>>>(
+        // un-mark the frontier's nodes on a side stream: it overlaps whatever the caller enqueues next (the feature
+        // gather) instead of delaying it; the next k-hop waits for it (reset_done)
+        QV_CUDA(cudaStreamWaitEvent(s->side_stream, s->meta_ready, 0));
+        map_reset_kernel<<<grid_for(bn[n_hops], 256, s->n_sm), 256, 0, s->side_stream>>>(
             n_id, s->d_meta + kMetaStride * (n_hops - 1) + kMetaF, map, s->n_nodes);
         QV_CHECK_LAUNCH("map_reset_kernel");
+        QV_CUDA(cudaEventRecord(s->reset_done, s->side_stream));
+        s->reset_pending = true;
     }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
     if (use_map) {
