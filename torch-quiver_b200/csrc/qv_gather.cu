@@ -16,6 +16,7 @@
 //     output rows are contiguous.  No registers touch the payload.  Needs row_bytes % 16 == 0.
 //   * ids outside [0, rows) and inaccessible shards produce zero rows (the reference leaves them uninitialised).
 #include <algorithm>
+#include <cstdlib>
 
 #include "qv_common.cuh"
 
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(256)
 // Same batching, but the 32 rows of a warp are walked as ONE flat run of chunks (chunk f -> row f / cpr, column
 // f % cpr, exact 32-bit multiply-high division), so rows whose chunk count is not a multiple of the group width keep
 // every lane busy: 400-byte rows (25 chunks) use 32/32 lanes instead of 25/32.
-template <int kLoad, int kStore>
-__global__ void __launch_bounds__(256, 5)
+template <int kLoad, int kStore, int kUnroll = kBatchUnroll, int kMinBlocks = 5>
+__global__ void __launch_bounds__(256, kMinBlocks)
     gather_batch_flat_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
                              const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, uint32_t cpr,
                              uint32_t inv, char *__restrict__ out)
@@ -228,13 +229,13 @@ __global__ void __launch_bounds__(256, 5)
     const uint32_t total = rows_here * cpr;
     char *out_base = out + base * row_bytes;
 
-    for (uint32_t f0 = 0; f0 < total; f0 += 32 * kBatchUnroll) {
-        const char *src[kBatchUnroll];
-        uint32_t off[kBatchUnroll];  // byte offset of the chunk inside the warp's output run
-        uint32_t col[kBatchUnroll];
-        bool live[kBatchUnroll];
+    for (uint32_t f0 = 0; f0 < total; f0 += 32 * kUnroll) {
+        const char *src[kUnroll];
+        uint32_t off[kUnroll];  // byte offset of the chunk inside the warp's output run
+        uint32_t col[kUnroll];
+        bool live[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kBatchUnroll; u++) {
+        for (int u = 0; u < kUnroll; u++) {
             const uint32_t f = f0 + u * 32 + lane;
             live[u] = f < total;
             const uint32_t row = live[u] ? __umulhi(f, inv) : 0;  // exact: f * cpr < 2^32 (host-checked)
@@ -243,12 +244,12 @@ __global__ void __launch_bounds__(256, 5)
             const unsigned long long p = __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(my_src), row);
             src[u] = reinterpret_cast<const char *>(p);
         }
-        typename L::T v[kBatchUnroll];
+        typename L::T v[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kBatchUnroll; u++)
+        for (int u = 0; u < kUnroll; u++)
             v[u] = (live[u] && src[u]) ? L::load(src[u] + static_cast<size_t>(col[u]) * kLoad) : L::zero();
 #pragma unroll
-        for (int u = 0; u < kBatchUnroll; u++) {
+        for (int u = 0; u < kUnroll; u++) {
             if (live[u]) {
                 char *dst = out_base + off[u];
                 if constexpr (kLoad == kStore) {
@@ -440,6 +441,8 @@ int launch_batch(const GatherParams &p, const int64_t *indices, const int64_t *f
     if ((cpr & (cpr - 1)) != 0 && (cpr % 32) != 0 && cpr <= 8192 && row_bytes * 32 < (int64_t(1) << 31)) {
         // rows that would leave lanes idle in the grouped kernel: flat walk (32 * cpr * cpr < 2^32 holds)
         const uint32_t inv = static_cast<uint32_t>((uint64_t(1) << 32) / static_cast<uint64_t>(cpr)) + 1u;
+        // (rows in flight per lane, min blocks per SM) = (4, 5): a sweep over {2,4,8} x {3..8} stayed within 0.75-0.79
+        // of the HBM peak on 400-byte rows -- the kernel sits on the DRAM random-access limit, not on occupancy
         gather_batch_flat_kernel<kLoad, kStore><<<g, 256, 0, st>>>(p, indices, feature_order, n, rb,
                                                                     static_cast<uint32_t>(cpr), inv, out);
         QV_CHECK_LAUNCH("gather_batch_flat_kernel");
