@@ -331,8 +331,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   * the ids to emit (verbatim rows and chosen positions alike) are handled as ONE flat list of <= 16*k entries per
 //     warp -- 32 lanes wide instead of k lanes wide -- fetched with cp.async into a staging tile (verbatim rows before
 //     the generator loop even starts) and written out after a single wait.
-template <bool kShortTable>
-__global__ void __launch_bounds__(kSampleWarps * 32)
+template <bool kShortTable, int kHub, int kMinBlocks>
+__global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     sample_rows_small_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
                              const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int k,
                              const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
@@ -341,18 +341,24 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
                              const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t item_base_arg,
                              const int64_t *__restrict__ d_item_base, int64_t *__restrict__ d_err)
 {
-    __shared__ uint32_t slots_sh[kSampleWarps][kRowsPerWarp][32];
-    __shared__ int64_t stage_sh[kSampleWarps][kRowsPerWarp * 32];
+    // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
+    // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    const uint32_t kcap = k > 0 ? static_cast<uint32_t>(k) : 1u;
+    const uint32_t per_warp = kRowsPerWarp * kcap;
     __shared__ int64_t start_sh[kSampleWarps][kRowsPerWarp];
     __shared__ int64_t o_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint32_t deg_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
-    __shared__ uint8_t rowof_sh[kSampleWarps][kRowsPerWarp * 32];  // entry -> row
     const int64_t S = dev_size(S_arg, d_S);
     const int64_t b = blockIdx.x;
     if (b * kSampleTile >= S) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t kk = static_cast<uint32_t>(k);
+    int64_t *stage_w = reinterpret_cast<int64_t *>(dyn_smem) + static_cast<size_t>(w) * per_warp;
+    uint32_t *slots_w = reinterpret_cast<uint32_t *>(dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 8) +
+                        static_cast<size_t>(w) * per_warp;
+    uint8_t *rowof_w = dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 12 + static_cast<size_t>(w) * per_warp;
 
     Xorwow rng;
     {
@@ -395,17 +401,16 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             start_sh[w][lane] = my_start;
             o_sh[w][lane] = my_o;
             pre_sh[w][lane] = static_cast<uint16_t>(incl - cnt);
-            for (uint32_t j = 0; j < cnt; j++) rowof_sh[w][incl - cnt + j] = static_cast<uint8_t>(lane);
+            for (uint32_t j = 0; j < cnt; j++) rowof_w[incl - cnt + j] = static_cast<uint8_t>(lane);
         }
     }
-#pragma unroll
-    for (int i = 0; i < kRowsPerWarp; i++) slots_sh[w][i][lane] = lane;
+    for (uint32_t e = lane; e < per_warp; e += 32) slots_w[e] = e % kcap;  // every reservoir starts as 0..k-1
     __syncwarp();
 
     // verbatim rows: their ids can start travelling now
     for (uint32_t e = lane; e < n_entries; e += 32) {
-        const int i = rowof_sh[w][e];
-        if (deg_sh[w][i] <= kk) cp_async_8(&stage_sh[w][e], indices + start_sh[w][i] + (e - pre_sh[w][i]));
+        const int i = rowof_w[e];
+        if (deg_sh[w][i] <= kk) cp_async_8(&stage_w[e], indices + start_sh[w][i] + (e - pre_sh[w][i]));
     }
 
     // this lane's generator stream, row after row, no synchronisation
@@ -417,40 +422,40 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             const uint32_t d = deg_sh[w][i];
             if (d <= first) continue;
             uint32_t rem = (d - first + 31) >> 5, idx = first;
-            uint32_t *srow = slots_sh[w][i];
-            if (rem >= 8 && idx + 512 < tab_n) {
-                unsigned long long M[8];
+            uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
+            if (rem >= kHub && idx + 64 * kHub < tab_n) {
+                unsigned long long M[kHub];
 #pragma unroll
-                for (int u = 0; u < 8; u++) M[u] = tab[idx + 32 * u];
+                for (int u = 0; u < kHub; u++) M[u] = tab[idx + 32 * u];
                 while (true) {
-                    unsigned long long N[8];
-                    const bool more = rem >= 16 && idx + 768 < tab_n;
+                    unsigned long long N[kHub];
+                    const bool more = rem >= 2 * kHub && idx + 96 * kHub < tab_n;
                     if (more) {
 #pragma unroll
-                        for (int u = 0; u < 8; u++) N[u] = tab[idx + 256 + 32 * u];
+                        for (int u = 0; u < kHub; u++) N[u] = tab[idx + 32 * kHub + 32 * u];
                     }
-                    uint32_t r[8];
+                    uint32_t r[kHub];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) r[u] = xorwow_next(rng);
+                    for (int u = 0; u < kHub; u++) r[u] = xorwow_next(rng);
                     bool cand = false;
-                    unsigned long long low[8];
+                    unsigned long long low[kHub];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < kHub; u++) {
                         low[u] = M[u] * r[u];
                         cand |= low[u] < M[u] * kk;
                     }
                     if (cand) {
 #pragma unroll
-                        for (int u = 0; u < 8; u++) {
+                        for (int u = 0; u < kHub; u++) {
                             const uint32_t num = static_cast<uint32_t>(__umul64hi(low[u], idx + 32 * u + 1));
                             if (num < kk) atomicMax(&srow[num], idx + 32 * u);
                         }
                     }
-                    idx += 256;
-                    rem -= 8;
+                    idx += 32 * kHub;
+                    rem -= kHub;
                     if (!more) break;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) M[u] = N[u];
+                    for (int u = 0; u < kHub; u++) M[u] = N[u];
                 }
             }
             if (kShortTable) {
@@ -480,17 +485,17 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
 
     // sampled rows: fetch the chosen positions; then one wait and one coalesced write-out of the whole list
     for (uint32_t e = lane; e < n_entries; e += 32) {
-        const int i = rowof_sh[w][e];
+        const int i = rowof_w[e];
         if (deg_sh[w][i] > kk)
-            cp_async_8(&stage_sh[w][e], indices + start_sh[w][i] + slots_sh[w][i][e - pre_sh[w][i]]);
+            cp_async_8(&stage_w[e], indices + start_sh[w][i] + slots_w[static_cast<size_t>(i) * kcap + (e - pre_sh[w][i])]);
     }
     cp_async_wait_all();
     const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
     const int64_t item_base = node_map ? (d_item_base ? *d_item_base : item_base_arg) : 0;
     for (uint32_t e = lane; e < n_entries; e += 32) {
-        const int i = rowof_sh[w][e];
+        const int i = rowof_w[e];
         const int64_t dst = o_sh[w][i] + (e - pre_sh[w][i]);
-        const int64_t id = stage_sh[w][e];
+        const int64_t id = stage_w[e];
         out[dst] = id;
         if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
         if (node_map) {  // fused k-hop: the sampled id enters the first-occurrence map right here
@@ -1068,13 +1073,14 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     QV_REQUIRE(blocks < (int64_t(1) << 31), "sample: too many seeds (%lld)", (long long)S_bound);
     const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n};
     static const int impl = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;  // tuning switch
+    const size_t small_smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max<int64_t>(k, 1) * 13;
     if (k >= 0 && k <= 32 && !(impl & 1)) {
         if (!(impl & 4))  // default: fastmod table for short rows too (measured -10 us per bench step vs plain %)
-            sample_rows_small_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            sample_rows_small_kernel<true, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
                 row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err);
         else
-            sample_rows_small_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
+            sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
                 row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
