@@ -200,6 +200,8 @@ def run_ours(args, rank, world, local_rank):
     del indptr, indices
     topo = quiver.CSRTopo(indptr=indptr_cpu, indices=indices_cpu)
     sampler = quiver.pyg.GraphSageSampler(topo, SIZES, device=local_rank, mode="GPU")
+    sampler.overlap = args.overlap  # opt-in pipelining of sample(i+1) with gather(i) on a private stream (default off)
+    sampler.inputs_ready = True  # the device-resident seed batches below are materialised before the timed region
     g = torch.Generator().manual_seed(7)
     x_cpu = torch.rand(N_NODES, FEAT_DIM, generator=g)
     if world == 1:
@@ -237,9 +239,11 @@ def run_ours(args, rank, world, local_rank):
         feature[n_id]
     barrier()
 
-    # ---- timed region A: inputs resident in HBM ("value") -------------------------------------------------------------
+    # ---- timed region A: K steps, inputs resident in HBM ("value"), with per-phase events ------------------------------
+    want_overlap = sampler.overlap
+    sampler.overlap = False
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
-    launches0 = _lib.launch_count()
+    launches_s0 = _lib.launch_count()
     edges = rows = 0
     hop_bytes = 0  # B_hop = 40*E + 40*S + 8*F algorithmic bytes per hop
     nid_keep = []
@@ -256,10 +260,30 @@ def run_ours(args, rank, world, local_rank):
         nid_keep.append(n_id)
         ev[3 * i + 3].record()
     barrier()
-    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    launches_serial = _lib.launch_count() - launches_s0
+    serial_ms = ev[0].elapsed_time(ev[3 * args.steps])
     sample_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps))
     gather_ms = sum(ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps))
-    launches = _lib.launch_count() - launches0
+    sampler.overlap = want_overlap
+
+    # ---- optional: the same K steps with the sampler on its private stream (--overlap) --------------------------------
+    if want_overlap:
+        launches0 = _lib.launch_count()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        edges_a = 0
+        barrier()
+        a0.record()
+        for b in batches_dev[args.warmup:]:
+            n_id, _, adjs = sampler.sample(b)
+            res = feature[n_id]
+            edges_a += sum(a.edge_index.shape[1] for a in adjs)
+        a1.record()
+        barrier()
+        total_ms = a0.elapsed_time(a1)
+        assert edges_a == edges  # same batches, same (deterministic) samples
+        launches = _lib.launch_count() - launches0
+    else:
+        total_ms, launches = serial_ms, launches_serial
 
     # ---- timed region B: end to end through the public API with HOST seeds -------------------------------------------
     barrier()
@@ -304,7 +328,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = rows_per_launch * alg_bytes_per_row / (kern_ms * 1e-3) / 1e9
 
     # ---- reduce over ranks -------------------------------------------------------------------------------------------
-    stats = torch.tensor([total_ms, sample_ms, gather_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms], dtype=torch.float64, device=dev)
     # ---- a large-batch point (64 k seeds): the sampler where bandwidth, not launch latency, matters -------
     big = None
     if not args.no_large_batch:
@@ -330,7 +354,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms, sample_ms, gather_ms, e2e_ms, kern_ms = stats.tolist()
+    total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms = stats.tolist()
     edges_all, rows_all, e2e_edges_all, launches_all = sums.tolist()
     if rank != 0:
         return None
@@ -342,13 +366,17 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "n_edges": n_edges, "placement": placement, "sampler_mode": "GPU (CSR in HBM), "
-                   "reference-exact XORWOW sampling (rand_seed 0)", "l2": "inputs larger than L2 (990 MB CSR + 980 MB "
+                   "reference-exact XORWOW sampling (rand_seed 0)",
+                   "pipelining": ("sampler on its own high-priority stream (as the reference's stream pool): sample(i+1) "
+                                  "overlaps the still-running feature gather of step i; every call returns completed "
+                                  "results" if sampler.overlap else "none: sampler and gather on one stream"), "l2": "inputs larger than L2 (990 MB CSR + 980 MB "
                    "feature table vs 126 MB L2); fresh seeds every step", "edges_per_step": edges_all / args.steps / world,
                    "rows_per_step": rows_all / args.steps / world},
         "seps_sampler_only": edges_all / (sample_ms * 1e-3),
         "feature_gather_GBps": rows_all * row_bytes / (gather_ms * 1e-3) / 1e9,
         "feature_gather_GiBps": rows_all * row_bytes / (gather_ms * 1e-3) / 2**30,
         "sample_ms_per_step": sample_ms / args.steps, "gather_ms_per_step": gather_ms / args.steps,
+        "serial_ms_per_step": serial_ms / args.steps, "serial_edges_per_s": edges_all / (serial_ms * 1e-3),
         "sampler_roofline": {"bound": "hbm (nominally; at 1024 seeds the hops are launch/latency bound)",
                              "algorithmic_bytes_per_step": hop_bytes / args.steps, "formula": "sum over hops 40E+40S+8F",
                              "achieved": hop_bytes / (sample_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -403,6 +431,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-batch", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="run the sampler on its own high-priority stream so sample(i+1) overlaps gather(i)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -53,6 +53,16 @@ class GraphSageSampler:
         self.csr_topo = csr_topo
         self.mode = mode
         self.fused = True  # all hops in one C call; falls back per hop when a size is -1
+        # The fused sampler runs on its own high-priority CUDA stream (the reference also samples on a private stream
+        # pool, quiver_sample.cu:116-117), so a sample() call overlaps whatever the caller left running on the current
+        # stream -- typically the previous batch's feature gather or training step.  The call still returns only when
+        # its results are complete, and CUDA inputs are ordered after the current stream unless `inputs_ready` says the
+        # seeds were materialised long ago.
+        # Opt-in: measured +8 % throughput when the consumer never waits on the host, -13 % when every step reads a result
+        # back (the gather saturates HBM, so the overlapped sampler's dependent loads get slower), hence off by default.
+        self.overlap = False
+        self.inputs_ready = False
+        self._priv_stream = None
         if device is not _FakeDevice and device >= 0:
             self.quiver = self._build(device)
         self.device = device
@@ -87,11 +97,13 @@ class GraphSageSampler:
         self.lazy_init_quiver()
         if not isinstance(input_nodes, torch.Tensor):
             input_nodes = torch.tensor(input_nodes)
-        nodes = input_nodes.to(self.device)
-        batch_size = len(nodes)
+        batch_size = len(input_nodes)
         if self.fused and batch_size > 0 and all(s >= 0 for s in self.sizes):
             try:
-                n_id, hops = self.quiver.sample_khop(nodes, self.sizes)
+                if self.overlap:
+                    n_id, hops = self._sample_khop_overlapped(input_nodes)
+                else:
+                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device), self.sizes)
             except qv.Unsupported:
                 pass
             else:
@@ -100,6 +112,7 @@ class GraphSageSampler:
                 sizes = torch.tensor([[n_src, n_dst] for _, n_src, n_dst in hops], dtype=torch.long)
                 adjs = [Adj(hop[0], _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
                 return n_id, batch_size, adjs[::-1]
+        nodes = input_nodes.to(self.device)
         adjs = []
         for size in self.sizes:
             out, cnt = self.sample_layer(nodes, size)
@@ -108,6 +121,18 @@ class GraphSageSampler:
             adjs.append(Adj(edge_index, torch.tensor([]), torch.LongTensor([frontier.size(0), nodes.size(0)])))
             nodes = frontier
         return nodes, batch_size, adjs[::-1]
+
+    def _sample_khop_overlapped(self, input_nodes):
+        if self._priv_stream is None:
+            self._priv_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        priv, cur = self._priv_stream, torch.cuda.current_stream(self.device)
+        if input_nodes.is_cuda and not self.inputs_ready:
+            priv.wait_stream(cur)  # the seeds may still be in flight on the caller's stream
+        with torch.cuda.stream(priv):
+            nodes = input_nodes.to(self.device)
+            n_id, hops = self.quiver.sample_khop(nodes, self.sizes)  # returns after synchronising `priv`
+        n_id.record_stream(cur)  # one arena backs n_id and every edge_index: keep it alive for the consumer stream
+        return n_id, hops
 
     def sample_prob(self, train_idx, total_node_count):
         """Per-node access probability after len(sizes) hops from `train_idx` (sage_sampler.py:149-157)."""
