@@ -289,3 +289,60 @@ def test_products_scale_properties():
         assert bool((key[pos.clamp(max=E - 1)] == ekey).all())
         n_dst = int(adj.size[0])
     assert n_dst == n_id.numel()
+
+
+@pytest.mark.parametrize("k", [31, 32, 33])
+def test_small_kernel_boundary_and_multigraph(oracle, k):
+    """Fan-outs around the 32-wide kernel switch, on a multigraph (duplicate neighbour ids inside a row, unsorted rows)."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    deg = rng.integers(0, 200, n)
+    deg[:5] = [0, 1, 31, 32, 33]
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, 40, int(indptr[-1])).astype(np.int64)  # ids from a tiny range: heavy duplication
+    q = _quiver(indptr, indices)
+    seeds = np.concatenate([np.arange(5), rng.integers(0, n, 700)])
+    out, cnt = q.sample_neighbor(0, _dev(seeds), k)
+    ref_out, ref_cnt = oracle.sample_neighbor(indptr, indices, seeds, k)
+    assert torch.equal(cnt.cpu(), torch.from_numpy(ref_cnt)) and torch.equal(out.cpu(), torch.from_numpy(ref_out))
+    assert oracle.validate_sample(indptr, indices, seeds, k, ref_cnt, out.cpu().numpy()) == 0
+    f, r, c = q.sample_sub(0, _dev(seeds), k)  # Quiver.sample_sub == sample_neighbor + reindex_single
+    of, orow, ocol = oracle.reindex(seeds, ref_out, ref_cnt)
+    assert torch.equal(f.cpu(), torch.from_numpy(of)) and torch.equal(r.cpu(), torch.from_numpy(orow))
+    assert torch.equal(c.cpu(), torch.from_numpy(ocol))
+
+
+def test_fused_khop_in_uva_mode(oracle):
+    import quiver
+    indptr, indices = powerlaw_csr(15000, 20.0, seed=15)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [8, 4, 2], device=0, mode="UVA")  # indices read zero-copy from host
+    seeds = np.random.default_rng(5).permutation(15000)[:400]
+    n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+    o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [8, 4, 2])
+    assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+    for adj, (o_ei, _) in zip(adjs, o_adjs):
+        assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei))
+
+
+def test_overlapped_sampling_gives_identical_results(oracle):
+    import quiver
+    indptr, indices = powerlaw_csr(12000, 18.0, seed=16)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [10, 5], device=0, mode="GPU")
+    sampler.overlap = True  # private high-priority stream
+    x = torch.randn(12000, 64)
+    feature = quiver.Feature(0, [0], device_cache_size="1G")
+    feature.from_cpu_tensor(x)
+    rng = np.random.default_rng(6)
+    keep = []
+    for it in range(5):
+        seeds = rng.permutation(12000)[:512]
+        n_id, _, adjs = sampler.sample(torch.from_numpy(seeds) if it % 2 else torch.from_numpy(seeds).cuda())
+        keep.append((seeds, n_id, adjs, feature[n_id]))  # the gather runs while the next sample() is issued
+    for seeds, n_id, adjs, rows in keep:
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [10, 5])
+        assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+        assert all(torch.equal(a.edge_index.cpu(), torch.from_numpy(o[0])) for a, o in zip(adjs, o_adjs))
+        assert torch.equal(rows.cpu(), x[torch.from_numpy(o_nid)])
