@@ -44,6 +44,28 @@ __device__ __forceinline__ int64_t dev_size(int64_t arg, const int64_t *d)
     return d ? *d : arg;
 }
 
+// Programmatic dependent launch: the kernels of a k-hop form a strict chain of short launches; launching each with the
+// programmatic-serialization attribute lets its blocks be scheduled while the previous kernel drains, and this wait
+// (a no-op for ordinary launches) holds them until the predecessor's writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    static const bool enabled = !(getenv("QV_PDL") && getenv("QV_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = enabled ? 1 : 0;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Single-pass chained scan (decoupled look-back).  Tile descriptors: bits 63..62 = flag, 61..0 = value.
 // Tiles take their index from an atomic ticket so a tile only ever waits on tiles that are already running.
@@ -164,6 +186,7 @@ __global__ void __launch_bounds__(kScanThreads)
                       int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles,
                       const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t *__restrict__ d_err)
 {
+    pdl_wait();
     const int64_t S = dev_size(S_arg, d_S);
     const int tile = take_ticket(st);
     const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
@@ -350,6 +373,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     __shared__ int64_t o_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint32_t deg_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
+    pdl_wait();
     const int64_t S = dev_size(S_arg, d_S);
     const int64_t b = blockIdx.x;
     if (b * kSampleTile >= S) return;
@@ -733,6 +757,7 @@ __global__ void __launch_bounds__(256)
                       const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
                       int64_t n_nodes, int64_t *__restrict__ d_err)
 {
+    pdl_wait();
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -758,6 +783,7 @@ __global__ void __launch_bounds__(kScanThreads)
                     int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg,
                     int64_t *__restrict__ d_next_S)
 {
+    pdl_wait();
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
     const long long F_prev = d_F_prev ? *d_F_prev : 0;
@@ -808,6 +834,7 @@ __global__ void __launch_bounds__(256)
     map_emit_kernel(const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, const int *__restrict__ map,
                     int64_t n_nodes, int64_t *__restrict__ col_idx)
 {
+    pdl_wait();
     const int64_t E = *d_E;
     for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
          e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -1054,9 +1081,9 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
                       const HopExtras &x = HopExtras())
 {
     const int n_tiles = tiles_for(S_bound);
-    count_scan_kernel<<<n_tiles, kScanThreads, 0, st>>>(s->indptr, s->n_nodes, seeds, S_arg, d_S, k, counts, out_ptr,
-                                                         d_total, scan_region(s, region), n_tiles, x.cached_deg,
-                                                         x.cached_deg ? nullptr : x.node_map, x.d_err);
+    QV_CUDA(launch_chained(count_scan_kernel, n_tiles, kScanThreads, 0, st, s->indptr, s->n_nodes, seeds, S_arg, d_S, k,
+                           counts, out_ptr, d_total, scan_region(s, region), n_tiles, x.cached_deg,
+                           x.cached_deg ? nullptr : x.node_map, x.d_err));
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
 }
@@ -1076,9 +1103,10 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     const size_t small_smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max<int64_t>(k, 1) * 13;
     if (k >= 0 && k <= 32 && !(impl & 1)) {
         if (!(impl & 4))  // default: fastmod table for short rows too (measured -10 us per bench step vs plain %)
-            sample_rows_small_kernel<true, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
-                s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-                row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err);
+            QV_CUDA(launch_chained(sample_rows_small_kernel<true, 4, 8>, static_cast<unsigned>(blocks), kSampleWarps * 32,
+                                   small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
+                                   static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
+                                   x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err));
         else
             sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
@@ -1377,8 +1405,8 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             const int64_t *prefix = h == 0 ? seeds : nullptr;
             const int64_t items = (h == 0 ? bn[0] : 0) + be[h];
             if (items > 0 && !fused_insert) {  // fan-outs > 32 use the generic sampling kernel, which does not insert
-                map_insert_kernel<<<grid_for(items, 256, s->n_sm), 256, 0, st>>>(prefix, 0, d_S, nbr, d_E, map,
-                                                                                  s->n_nodes, d_err);
+                QV_CUDA(launch_chained(map_insert_kernel, grid_for(items, 256, s->n_sm), 256, 0, st, prefix, 0, d_S, nbr,
+                                       d_E, map, s->n_nodes, d_err));
                 QV_CHECK_LAUNCH("map_insert_kernel");
             }
             int64_t *fs = h + 1 < n_hops ? fr_start : nullptr, *fd = h + 1 < n_hops ? fr_deg : nullptr;
@@ -1390,14 +1418,14 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                                                                        fd, d_next_S);
             } else {
                 const int n_tiles = tiles_for(items);
-                map_scan_kernel<4><<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
-                                                                      h == 0 ? nullptr : d_S, n_id, d_F,
-                                                                      scan_region(s, 2 * h + 1), n_tiles, s->indptr, fs, fd,
-                                                                      d_next_S);
+                QV_CUDA(launch_chained(map_scan_kernel<4>, n_tiles, kScanThreads, 0, st, prefix, 0, d_S, nbr, d_E, map,
+                                       s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles,
+                                       s->indptr, fs, fd, d_next_S));
             }
             QV_CHECK_LAUNCH("map_scan_kernel");
             if (be[h] > 0) {
-                map_emit_kernel<<<grid_for(be[h], 256, s->n_sm), 256, 0, st>>>(nbr, d_E, map, s->n_nodes, edge_buf[h]);
+                QV_CUDA(launch_chained(map_emit_kernel, grid_for(be[h], 256, s->n_sm), 256, 0, st, nbr, d_E, map,
+                                       s->n_nodes, edge_buf[h]));
                 QV_CHECK_LAUNCH("map_emit_kernel");
             }
         }
