@@ -48,6 +48,13 @@ __device__ __forceinline__ int64_t dev_size(int64_t arg, const int64_t *d)
 // programmatic-serialization attribute lets its blocks be scheduled while the previous kernel drains, and this wait
 // (a no-op for ordinary launches) holds them until the predecessor's writes are visible.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Short kernels additionally release their dependents right away: the next kernel's blocks become resident (parked in
+// pdl_wait) while this one still runs, so the hand-over costs no launch latency at all.
+__device__ int g_pdl_early = 1;
+__device__ __forceinline__ void pdl_release()
+{
+    if (g_pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(kScanThreads)
                       const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t *__restrict__ d_err)
 {
     pdl_wait();
+    pdl_release();
     const int64_t S = dev_size(S_arg, d_S);
     const int tile = take_ticket(st);
     const int64_t base = static_cast<int64_t>(tile) * kScanTile + threadIdx.x * kScanItems;
@@ -758,6 +766,7 @@ __global__ void __launch_bounds__(256)
                       int64_t n_nodes, int64_t *__restrict__ d_err)
 {
     pdl_wait();
+    pdl_release();
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -784,6 +793,7 @@ __global__ void __launch_bounds__(kScanThreads)
                     int64_t *__restrict__ d_next_S)
 {
     pdl_wait();
+    pdl_release();
     const int64_t P = prefix ? dev_size(P_arg, d_P) : 0, E = *d_E;
     const int64_t n = P + E;
     const long long F_prev = d_F_prev ? *d_F_prev : 0;
@@ -835,6 +845,7 @@ __global__ void __launch_bounds__(256)
                     int64_t n_nodes, int64_t *__restrict__ col_idx)
 {
     pdl_wait();
+    pdl_release();
     const int64_t E = *d_E;
     for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
          e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -1222,6 +1233,11 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
             qv_sampler_destroy(s);
             return fail(QV_ERR_CUDA, "qv_sampler_create: %s", cudaGetErrorString(e));
         }
+    }
+    {
+        const char *env = getenv("QV_PDL_EARLY");
+        const int early = (env && env[0] == '0') ? 0 : 1;
+        cudaMemcpyToSymbol(g_pdl_early, &early, sizeof early);
     }
     *out = s;
     return QV_OK;
