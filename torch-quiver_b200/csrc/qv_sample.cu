@@ -1406,10 +1406,12 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         }
         bool fused_insert = false;
         QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
-        // Inserting the sampled ids into the node map from inside the sampling kernel was measured slower (+14 us on the
-        // kernel's critical blocks vs 9 us for a separate, perfectly parallel insert kernel): keep them separate.
+        // Inserting the sampled ids into the node map from inside the sampling kernel: for a large hop it was measured
+        // slower (+14 us on the kernel's critical blocks vs 9 us for a separate, perfectly parallel insert kernel), for a
+        // small hop it was neutral (saved launch vs longer kernel): off unless QV_FUSE_INSERT_BELOW is set.
+        static const int64_t fuse_below = getenv("QV_FUSE_INSERT_BELOW") ? atoll(getenv("QV_FUSE_INSERT_BELOW")) : 0;
         HopExtras xs = x;
-        xs.node_map = nullptr;
+        if (bn[h] > fuse_below) xs.node_map = nullptr;
         // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
         QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st, xs,
                              &fused_insert));
