@@ -238,6 +238,14 @@ def run_ours(args, rank, world, local_rank):
         n_id, _, adjs = sampler.sample(b)
         feature[n_id]
     barrier()
+    # The timed regions below last ~10 ms -- shorter than one nvidia-smi poll.  Keep the SAME step loop running for
+    # ~0.7 s first (untimed) so the clock / throttle record is taken under this workload's load.
+    t_probe = time.perf_counter()
+    while time.perf_counter() - t_probe < 0.7:
+        for b in batches_dev[args.warmup:]:
+            n_id, _, adjs = sampler.sample(b)
+            feature[n_id]
+    barrier()
 
     # ---- timed region A: K steps, inputs resident in HBM ("value"), with per-phase events ------------------------------
     want_overlap = sampler.overlap
