@@ -783,8 +783,8 @@ __global__ void __launch_bounds__(256)
 // kItems ids per thread: 4 for small hops, 16 for large ones -- the decoupled look-back advances ~32 tiles per L2 round
 // trip, so a 850 k-item hop cut into 830 tiles of 1024 spent most of its 18 us waiting on that chain; 208 tiles of
 // 4096 do not.
-template <int kItems>
-__global__ void __launch_bounds__(kScanThreads)
+template <int kItems, bool kRows>
+__global__ void __launch_bounds__(kScanThreads, kRows ? 4 : 6)
     map_scan_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
                     const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
                     int64_t n_nodes, const int64_t *__restrict__ d_F_prev, int64_t *__restrict__ frontier,
@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(kScanThreads)
 #pragma unroll
     for (int j = 0; j < kItems; j++) {
         rs[j] = rd[j] = 0;
-        if (first[j] && fr_deg) {
+        if (kRows && first[j]) {
             rs[j] = indptr[key[j]];
             rd[j] = indptr[key[j] + 1] - rs[j];
         }
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(kScanThreads)
         if (first[j]) {
             frontier[local] = key[j];
             map[key[j]] = static_cast<int>(static_cast<unsigned int>(local) | 0x80000000u);
-            if (fr_deg) {
+            if (kRows) {
                 fr_start[local] = rs[j];
                 fr_deg[local] = rd[j];
             }
@@ -1428,18 +1428,18 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                 QV_CHECK_LAUNCH("map_insert_kernel");
             }
             int64_t *fs = h + 1 < n_hops ? fr_start : nullptr, *fd = h + 1 < n_hops ? fr_deg : nullptr;
-            if (items > (int64_t(4) << 20)) {  // below that, more (smaller) tiles hide the random-load latency better
-                const int n_tiles = static_cast<int>((items + kScanThreads * 16 - 1) / (kScanThreads * 16));
-                map_scan_kernel<16><<<n_tiles, kScanThreads, 0, st>>>(prefix, 0, d_S, nbr, d_E, map, s->n_nodes,
-                                                                       h == 0 ? nullptr : d_S, n_id, d_F,
-                                                                       scan_region(s, 2 * h + 1), n_tiles, s->indptr, fs,
-                                                                       fd, d_next_S);
-            } else {
-                const int n_tiles = tiles_for(items);
-                QV_CUDA(launch_chained(map_scan_kernel<4>, n_tiles, kScanThreads, 0, st, prefix, 0, d_S, nbr, d_E, map,
-                                       s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles,
-                                       s->indptr, fs, fd, d_next_S));
-            }
+            const bool big = items > (int64_t(4) << 20);  // below that, more (smaller) tiles hide the random-load latency better
+            const int per_tile = kScanThreads * (big ? 16 : 4);
+            const int n_tiles = static_cast<int>(std::max<int64_t>(1, (items + per_tile - 1) / per_tile));
+#define QV_MAP_SCAN(ITEMS, ROWS)                                                                                         \
+    QV_CUDA(launch_chained(map_scan_kernel<ITEMS, ROWS>, n_tiles, kScanThreads, 0, st, prefix, 0, d_S, nbr, d_E, map,  \
+                           s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles, s->indptr,    \
+                           fs, fd, d_next_S))
+            if (big && fd) QV_MAP_SCAN(16, true);
+            else if (big) QV_MAP_SCAN(16, false);
+            else if (fd) QV_MAP_SCAN(4, true);
+            else QV_MAP_SCAN(4, false);
+#undef QV_MAP_SCAN
             QV_CHECK_LAUNCH("map_scan_kernel");
             if (be[h] > 0) {
                 QV_CUDA(launch_chained(map_emit_kernel, grid_for(be[h], 256, s->n_sm), 256, 0, st, nbr, d_E, map,

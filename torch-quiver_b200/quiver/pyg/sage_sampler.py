@@ -103,7 +103,7 @@ class GraphSageSampler:
                 if self.overlap:
                     n_id, hops = self._sample_khop_overlapped(input_nodes)
                 else:
-                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device), self.sizes)
+                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes)
             except qv.Unsupported:
                 pass
             else:
