@@ -185,13 +185,30 @@ __device__ __forceinline__ int take_ticket(ScanState st)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Epoch-tagged node map of the fused k-hop (one 64-bit word per graph node, never reset).
+//   word = (0xFFFFFFFF - epoch) << 32 | payload ; a sample() call uses a fresh epoch, so every word written by an earlier
+//   call compares LARGER than anything written now and a plain 64-bit atomicMin overwrites it: no clearing pass, no
+//   dependence on the caller's buffers after the call returns.  Within a call:
+//     payload = local id            (< 2^31)      the node is in the frontier
+//     payload = 2^31 + item index                 candidate: smallest item index that sampled it in this hop
+//   so min() keeps a known node known and otherwise elects the first occurrence.  memset(0xFF) = "never seen".
+// ------------------------------------------------------------------------------------------------------------------
+using MapWord = unsigned long long;
+constexpr unsigned int kMapCand = 0x80000000u;
+__device__ __forceinline__ MapWord map_word(unsigned int epoch_hi, unsigned int payload)
+{
+    return (static_cast<MapWord>(epoch_hi) << 32) | payload;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Kernel A: counts[i] = min(deg(seed_i), k), out_ptr = exclusive scan, total.   (quiver_sample.cu:157-169)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
     count_scan_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, const int64_t *__restrict__ seeds,
                       int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k, int64_t *__restrict__ counts,
                       int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles,
-                      const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t *__restrict__ d_err)
+                      const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
+                      int64_t *__restrict__ d_err)
 {
     pdl_wait();
     pdl_release();
@@ -213,7 +230,8 @@ __global__ void __launch_bounds__(kScanThreads)
                 if (node >= 0 && node < n_nodes) {
                     const int64_t deg = indptr[node + 1] - indptr[node];
                     v = (k >= 0 && deg > k) ? k : deg;
-                    if (node_map) atomicMin(&node_map[node], static_cast<int>(i));  // hop 0: seeds enter the node map
+                    if (node_map)  // hop 0: seeds enter the node map
+                        atomicMin(&node_map[node], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(i)));
                 } else if (node_map) {
                     *d_err = 1;
                 }
@@ -369,8 +387,9 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                              const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states,
                              const RecipTable rt, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
                              const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
-                             const int64_t *__restrict__ cached_deg, int *__restrict__ node_map, int64_t item_base_arg,
-                             const int64_t *__restrict__ d_item_base, int64_t *__restrict__ d_err)
+                             const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
+                             int64_t item_base_arg, const int64_t *__restrict__ d_item_base,
+                             int64_t *__restrict__ d_err)
 {
     // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
     // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
@@ -532,7 +551,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
         if (node_map) {  // fused k-hop: the sampled id enters the first-occurrence map right here
             if (static_cast<uint64_t>(id) < static_cast<uint64_t>(n_nodes))
-                atomicMin(&node_map[id], static_cast<int>(item_base + dst));
+                atomicMin(&node_map[id], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(item_base + dst)));
             else
                 *d_err = 1;
         }
@@ -747,23 +766,17 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Fused k-hop reindex over a DIRECT node map (one int32 per graph node, kept across the hops of a sample() call).
+// Fused k-hop reindex over the epoch-tagged node map (see MapWord above), kept across the hops of a sample() call.
 // The frontier of hop h+1 is the frontier of hop h plus the not-yet-seen sampled nodes in first-occurrence order, with
 // unchanged local ids for the old ones -- so the hash table rebuilt from scratch every hop (reference:
-// quiver_sample.cu:202-255, one cudaMalloc+cudaMemset per call) is unnecessary inside a k-hop sample:
-//   map[v] = kMapUnseen             not in the frontier
-//   map[v] = i >= 0                 candidate: smallest item index of v among this hop's items (atomicMin)
-//   map[v] = local | 0x80000000     in the frontier with that local id (negative as int32: atomicMin never touches it)
-// Per hop only the E sampled ids are processed (not S+E), with 4-byte accesses and no probing; the map is reset for
-// the frontier's nodes after the last hop.  Ids outside [0, n_nodes) raise a flag and the call is redone on the
-// hash path (they can only come from invalid user seeds or a corrupt CSR).
+// quiver_sample.cu:202-255, one cudaMalloc+cudaMemset per call) is unnecessary inside a k-hop sample: per hop only the E
+// sampled ids are processed (not S+E), with one 8-byte access each and no probing.  Ids outside [0, n_nodes) raise a flag
+// and the call is redone on the hash path (they can only come from invalid user seeds or a corrupt CSR).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kMapUnseen = 0x7F7F7F7F;
-
 __global__ void __launch_bounds__(256)
     map_insert_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
-                      const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
-                      int64_t n_nodes, int64_t *__restrict__ d_err)
+                      const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, MapWord *__restrict__ map,
+                      unsigned int epoch_hi, int64_t n_nodes, int64_t *__restrict__ d_err)
 {
     pdl_wait();
     pdl_release();
@@ -776,20 +789,19 @@ __global__ void __launch_bounds__(256)
             *d_err = 1;
             continue;
         }
-        atomicMin(&map[key], static_cast<int>(i));
+        atomicMin(&map[key], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(i)));
     }
 }
 
-// kItems ids per thread: 4 for small hops, 16 for large ones -- the decoupled look-back advances ~32 tiles per L2 round
-// trip, so a 850 k-item hop cut into 830 tiles of 1024 spent most of its 18 us waiting on that chain; 208 tiles of
-// 4096 do not.
+// kItems ids per thread: 4 for small hops, 16 for very large ones (fewer tiles in the look-back chain).
+// kRows: also record the CSR row (start, degree) of every node that joins, for the next hop's count / sample kernels.
 template <int kItems, bool kRows>
 __global__ void __launch_bounds__(kScanThreads, kRows ? 4 : 6)
     map_scan_kernel(const int64_t *__restrict__ prefix, int64_t P_arg, const int64_t *__restrict__ d_P,
-                    const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, int *__restrict__ map,
-                    int64_t n_nodes, const int64_t *__restrict__ d_F_prev, int64_t *__restrict__ frontier,
-                    int64_t *__restrict__ d_F, ScanState st, int n_tiles, const int64_t *__restrict__ indptr,
-                    int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg,
+                    const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, MapWord *__restrict__ map,
+                    unsigned int epoch_hi, int64_t n_nodes, const int64_t *__restrict__ d_F_prev,
+                    int64_t *__restrict__ frontier, int64_t *__restrict__ d_F, ScanState st, int n_tiles,
+                    const int64_t *__restrict__ indptr, int64_t *__restrict__ fr_start, int64_t *__restrict__ fr_deg,
                     int64_t *__restrict__ d_next_S)
 {
     pdl_wait();
@@ -810,7 +822,7 @@ __global__ void __launch_bounds__(kScanThreads, kRows ? 4 : 6)
         if (i < n) {
             key[j] = i < P ? prefix[i] : outputs[i - P];
             if (static_cast<uint64_t>(key[j]) < static_cast<uint64_t>(n_nodes))
-                first[j] = map[key[j]] == static_cast<int>(i);
+                first[j] = map[key[j]] == map_word(epoch_hi, kMapCand + static_cast<unsigned int>(i));
         }
         sum += first[j] ? 1 : 0;
     }
@@ -830,7 +842,7 @@ __global__ void __launch_bounds__(kScanThreads, kRows ? 4 : 6)
     for (int j = 0; j < kItems; j++) {
         if (first[j]) {
             frontier[local] = key[j];
-            map[key[j]] = static_cast<int>(static_cast<unsigned int>(local) | 0x80000000u);
+            map[key[j]] = map_word(epoch_hi, static_cast<unsigned int>(local));
             if (kRows) {
                 fr_start[local] = rs[j];
                 fr_deg[local] = rd[j];
@@ -841,7 +853,7 @@ __global__ void __launch_bounds__(kScanThreads, kRows ? 4 : 6)
 }
 
 __global__ void __launch_bounds__(256)
-    map_emit_kernel(const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, const int *__restrict__ map,
+    map_emit_kernel(const int64_t *__restrict__ outputs, const int64_t *__restrict__ d_E, const MapWord *__restrict__ map,
                     int64_t n_nodes, int64_t *__restrict__ col_idx)
 {
     pdl_wait();
@@ -850,19 +862,9 @@ __global__ void __launch_bounds__(256)
     for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
          e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t key = outputs[e];
-        col_idx[e] = static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes) ? (map[key] & 0x7FFFFFFF) : 0;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-    map_reset_kernel(const int64_t *__restrict__ frontier, const int64_t *__restrict__ d_F, int *__restrict__ map,
-                     int64_t n_nodes)
-{
-    const int64_t F = *d_F;
-    for (int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; j < F;
-         j += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int64_t key = frontier[j];
-        if (static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes)) map[key] = kMapUnseen;
+        col_idx[e] = static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes)
+                         ? static_cast<int64_t>(static_cast<unsigned int>(map[key]) & 0x7FFFFFFFu)
+                         : 0;
     }
 }
 
@@ -985,9 +987,7 @@ struct qv_sampler {
 
     int64_t *d_meta = nullptr;  // kMetaWords device scalars
     int64_t *h_meta = nullptr;  // pinned mirror
-    cudaEvent_t meta_ready = nullptr, reset_done = nullptr;
-    cudaStream_t side_stream = nullptr;
-    bool reset_pending = false;
+    cudaEvent_t meta_ready = nullptr;
     Buffer scan;                // two scan-state regions
     size_t scan_region_words = 0;
     Buffer table;  // Slot[2^table_log2]
@@ -1000,8 +1000,8 @@ struct qv_sampler {
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
     Buffer fr_meta;   // [2][bound] int64: CSR row start / degree of every frontier node (fused k-hop path)
-    Buffer node_map;  // int32 per graph node: direct first-occurrence map of the fused k-hop path
-    bool map_ready = false, map_dirty = false;
+    Buffer node_map;  // MapWord per graph node: epoch-tagged first-occurrence map of the fused k-hop path
+    unsigned int map_epoch = 0;  // 0 = the map has never been initialised
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
     unsigned int recip_n = 0;
     int64_t max_degree = 0;
@@ -1081,7 +1081,8 @@ int rng_states_for(qv_sampler *s, uint64_t rand_seed, int64_t rows_arg, const in
 
 struct HopExtras {  // fused k-hop only; all null for the standalone calls
     const int64_t *cached_start = nullptr, *cached_deg = nullptr;
-    int *node_map = nullptr;
+    MapWord *node_map = nullptr;
+    unsigned int epoch_hi = 0;
     int64_t item_base = 0;
     const int64_t *d_item_base = nullptr;
     int64_t *d_err = nullptr;
@@ -1094,7 +1095,7 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
     const int n_tiles = tiles_for(S_bound);
     QV_CUDA(launch_chained(count_scan_kernel, n_tiles, kScanThreads, 0, st, s->indptr, s->n_nodes, seeds, S_arg, d_S, k,
                            counts, out_ptr, d_total, scan_region(s, region), n_tiles, x.cached_deg,
-                           x.cached_deg ? nullptr : x.node_map, x.d_err));
+                           x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err));
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
 }
@@ -1117,11 +1118,11 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
             QV_CUDA(launch_chained(sample_rows_small_kernel<true, 4, 8>, static_cast<unsigned>(blocks), kSampleWarps * 32,
                                    small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
                                    static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
-                                   x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err));
+                                   x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err));
         else
             sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-                row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.item_base, x.d_item_base, x.d_err);
+                row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
@@ -1196,8 +1197,6 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
     if (e == cudaSuccess) e = cudaMemset(s->d_meta, 0, kMetaWords * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_meta), kMetaWords * sizeof(int64_t), 0);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->meta_ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->reset_done, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         cudaGetLastError();
         if (s->d_meta) cudaFree(s->d_meta);
@@ -1262,8 +1261,6 @@ int qv_sampler_destroy(qv_sampler *s)
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
     if (s->meta_ready) cudaEventDestroy(s->meta_ready);
-    if (s->reset_done) cudaEventDestroy(s->reset_done);
-    if (s->side_stream) cudaStreamDestroy(s->side_stream);
     delete s;
     return QV_OK;
 }
@@ -1360,19 +1357,17 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
 {
     int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
     int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
-    int *map = static_cast<int *>(s->node_map.ptr);
+    MapWord *map = static_cast<MapWord *>(s->node_map.ptr);
     int64_t *d_err = s->d_meta + kMetaErr;
     *id_error = false;
+    unsigned int epoch_hi = 0;
     if (use_map) {
-        if (!s->map_ready || s->map_dirty) {
-            QV_CUDA(cudaMemsetAsync(map, 0x7F, static_cast<size_t>(std::max<int64_t>(s->n_nodes, 1)) * sizeof(int), st));
-            s->map_ready = true;
+        if (s->map_epoch == 0 || s->map_epoch >= 0xFFFFFFF0u) {  // first use, or the 32-bit epoch is about to wrap
+            QV_CUDA(cudaMemsetAsync(map, 0xFF, static_cast<size_t>(std::max<int64_t>(s->n_nodes, 1)) * sizeof(MapWord), st));
+            s->map_epoch = 0;
         }
-        s->map_dirty = true;
-    }
-    if (use_map && s->reset_pending) {  // the previous call's map reset ran on the side stream
-        QV_CUDA(cudaStreamWaitEvent(st, s->reset_done, 0));
-        s->reset_pending = false;
+        s->map_epoch++;  // every call (also a failed one) gets its own epoch: older words never need clearing
+        epoch_hi = 0xFFFFFFFFu - s->map_epoch;
     }
     init_khop_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, S, kMetaErr);
     QV_CHECK_LAUNCH("init_khop_meta_kernel");
@@ -1397,6 +1392,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start ? fr_start + bn[n_hops] : nullptr;
         if (use_map) {
             x.node_map = map;
+            x.epoch_hi = epoch_hi;
             x.d_err = d_err;
             x.d_item_base = h == 0 ? d_S : nullptr;  // items of hop 0 are [seeds | outputs]; later hops: outputs only
             if (h >= 1 && fr_start) {
@@ -1424,7 +1420,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             const int64_t items = (h == 0 ? bn[0] : 0) + be[h];
             if (items > 0 && !fused_insert) {  // fan-outs > 32 use the generic sampling kernel, which does not insert
                 QV_CUDA(launch_chained(map_insert_kernel, grid_for(items, 256, s->n_sm), 256, 0, st, prefix, 0, d_S, nbr,
-                                       d_E, map, s->n_nodes, d_err));
+                                       d_E, map, epoch_hi, s->n_nodes, d_err));
                 QV_CHECK_LAUNCH("map_insert_kernel");
             }
             int64_t *fs = h + 1 < n_hops ? fr_start : nullptr, *fd = h + 1 < n_hops ? fr_deg : nullptr;
@@ -1433,7 +1429,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             const int n_tiles = static_cast<int>(std::max<int64_t>(1, (items + per_tile - 1) / per_tile));
 #define QV_MAP_SCAN(ITEMS, ROWS)                                                                                         \
     QV_CUDA(launch_chained(map_scan_kernel<ITEMS, ROWS>, n_tiles, kScanThreads, 0, st, prefix, 0, d_S, nbr, d_E, map,  \
-                           s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles, s->indptr,    \
+                           epoch_hi, s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles, s->indptr,    \
                            fs, fd, d_next_S))
             if (big && fd) QV_MAP_SCAN(16, true);
             else if (big) QV_MAP_SCAN(16, false);
@@ -1449,26 +1445,9 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         }
     }
     QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    // the size read-back is complete once this event fires
     QV_CUDA(cudaEventRecord(s->meta_ready, st));
-    if (use_map) {
-        // un-mark the frontier's nodes on a side stream: it overlaps whatever the caller enqueues next (the feature
-        // gather) instead of delaying it; the next k-hop waits for it (reset_done)
-        QV_CUDA(cudaStreamWaitEvent(s->side_stream, s->meta_ready, 0));
-        map_reset_kernel<<<grid_for(bn[n_hops], 256, s->n_sm), 256, 0, s->side_stream>>>(
-            n_id, s->d_meta + kMetaStride * (n_hops - 1) + kMetaF, map, s->n_nodes);
-        QV_CHECK_LAUNCH("map_reset_kernel");
-        QV_CUDA(cudaEventRecord(s->reset_done, s->side_stream));
-        s->reset_pending = true;
-    }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
-    if (use_map) {
-        if (s->h_meta[kMetaErr] != 0) {
-            *id_error = true;  // map state is unspecified: force a clean one next time
-            return QV_OK;
-        }
-        s->map_dirty = false;
-    }
+    if (use_map && s->h_meta[kMetaErr] != 0) *id_error = true;  // the caller redoes the call on the hash path
     return QV_OK;
 }
 }  // namespace
@@ -1494,13 +1473,13 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
     }
     const char *env = getenv("QV_KHOP_REINDEX");  // "hash" forces the per-hop hash table (tests / A-B)
     bool use_map = !(env && env[0] == 'h') && s->n_nodes > 0 && s->n_nodes < (int64_t(1) << 31) &&
-                   bn[n_hops] < int64_t(kMapUnseen);
+                   s->n_nodes <= (int64_t(1) << 30) && bn[n_hops] < (int64_t(1) << 31);
     QV_TRY(ensure_scan(s, bn[n_hops]));
     QV_TRY(s->out_ptr.ensure(static_cast<size_t>(max_nodes) * sizeof(int64_t)));
     QV_TRY(s->nbr.ensure(static_cast<size_t>(std::max<int64_t>(max_edges, 1)) * sizeof(int64_t)));
     if (use_map && !s->node_map.ptr) {
-        if (s->node_map.ensure(static_cast<size_t>(s->n_nodes) * sizeof(int)) != QV_OK) use_map = false;  // no room
-        s->map_ready = false;
+        if (s->node_map.ensure(static_cast<size_t>(s->n_nodes) * sizeof(MapWord)) != QV_OK) use_map = false;  // no room
+        s->map_epoch = 0;
     }
     if (!use_map) QV_TRY(ensure_table(s, bn[n_hops]));
     const char *env_deg = getenv("QV_KHOP_CACHE_DEG");  // "0": re-read indptr per hop instead of caching (A-B switch)
