@@ -358,6 +358,25 @@ def run_ours(args, rank, world, local_rank):
                "frac_of_hbm_peak": big_bytes / (big_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_batch": big_ms / 3}
         del big_batches
 
+    # ---- informational: the opt-in fast (non-reference-stream) sampler on the same batches ------------------------------
+    fast = None
+    if not args.no_large_batch:
+        sampler.quiver.set_fast(True)
+        for b in batches_dev[:2]:
+            sampler.sample(b)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fe = 0
+        f0.record()
+        for b in batches_dev[args.warmup:]:
+            _, _, adjs = sampler.sample(b)
+            fe += sum(a.edge_index.shape[1] for a in adjs)
+        f1.record()
+        barrier()
+        fast = {"seps_sampler_only": fe / (f0.elapsed_time(f1) * 1e-3), "sample_ms_per_step": f0.elapsed_time(f1) / args.steps,
+                "note": "qv_sampler_set_fast: O(k) per row, NOT the reference's random stream; not part of `value`"}
+        sampler.quiver.set_fast(False)
+
     sums = torch.tensor([edges, rows, e2e_edges, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -389,6 +408,7 @@ def run_ours(args, rank, world, local_rank):
                              "algorithmic_bytes_per_step": hop_bytes / args.steps, "formula": "sum over hops 40E+40S+8F",
                              "achieved": hop_bytes / (sample_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hop_bytes / (sample_ms * 1e-3) / 1e9 / hbm_peak, "large_batch": big},
+        "fast_mode": fast,
         "gpu_launches": int(launches_all),
         "e2e": {"value": e2e_edges_all / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": BATCH * 8,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},

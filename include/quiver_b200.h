@@ -186,6 +186,12 @@ QV_API int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
 QV_API int qv_cal_neighbor_prob(qv_sampler *s, const float *last_prob, float *cur_prob, int64_t n, int k,
                          qv_stream_t stream);
 
+/* Extension (no reference counterpart): opt into position-independent O(k)-per-row sampling.  Same contract as
+ * CSRRowWiseSampleKernel (min(deg,k) distinct uniform positions, verbatim copy when deg <= k) but NOT the reference's
+ * random stream: ids differ from the reference's, and each call draws a fresh sample (seed = rand_seed + call counter).
+ * Default 0 = bit-identical to the reference under its generator seed. */
+QV_API int qv_sampler_set_fast(qv_sampler *s, int enabled);
+
 /* Diagnostics: number of kernel launches this library has issued in this process (bench.py "gpu_launches"). */
 QV_API int64_t qv_launch_count(void);
 

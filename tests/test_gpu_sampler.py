@@ -346,3 +346,63 @@ def test_overlapped_sampling_gives_identical_results(oracle):
         assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
         assert all(torch.equal(a.edge_index.cpu(), torch.from_numpy(o[0])) for a, o in zip(adjs, o_adjs))
         assert torch.equal(rows.cpu(), x[torch.from_numpy(o_nid)])
+
+
+def test_fast_mode_is_valid_uniform_and_not_the_reference_stream(oracle):
+    """Opt-in O(k)-per-row sampling (Quiver.set_fast): NOT bit-compatible with the reference -- checked at parity level L2
+    (SURVEY.md 8(c)): counts, membership, no duplicate positions, verbatim rows when deg <= k, uniformity, and the
+    reindex / k-hop structure around it."""
+    import quiver
+    indptr, indices = powerlaw_csr(20000, 40.0, seed=17, alpha=1.5)
+    q = _quiver(indptr, indices)
+    q.set_fast(True)
+    seeds = np.random.default_rng(8).permutation(20000)[:3000]
+    for k in (1, 5, 25, 40, 200, -1):
+        out, cnt = q.sample_neighbor(0, _dev(seeds), k)
+        ref_cnt, _, tot = oracle.sample_counts(indptr, seeds, k)
+        assert torch.equal(cnt.cpu(), torch.from_numpy(ref_cnt)) and out.numel() == tot
+        assert oracle.validate_sample(indptr, indices, seeds, k, ref_cnt, out.cpu().numpy()) == 0, k
+    out2, _ = q.sample_neighbor(0, _dev(seeds), 5)
+    out3, _ = q.sample_neighbor(0, _dev(seeds), 5)
+    assert not torch.equal(out2, out3)  # every call draws a fresh sample
+    ref5, _ = oracle.sample_neighbor(indptr, indices, seeds, 5)
+    assert not torch.equal(out2.cpu(), torch.from_numpy(ref5))
+    # uniformity: one row of degree 97 with distinct neighbour ids, k = 6, many calls
+    ip = np.array([0, 97], dtype=np.int64)
+    idx = np.arange(1000, 1097, dtype=np.int64)
+    q1 = _quiver(ip, idx)
+    q1.set_fast(True)
+    hits = np.zeros(97)
+    row = _dev(np.zeros(512, dtype=np.int64))  # 512 copies of the row per call: same node, different calls differ
+    trials = 0
+    for _ in range(40):
+        o, c = q1.sample_neighbor(0, row[:1], 6)
+        picks = o.cpu().numpy()
+        assert len(set(picks.tolist())) == 6
+        hits[picks - 1000] += 1
+        trials += 1
+    for _ in range(960):
+        o, _ = q1.sample_neighbor(0, row[:1], 6)
+        hits[o.cpu().numpy() - 1000] += 1
+        trials += 1
+    expect = trials * 6 / 97
+    chi2 = ((hits - expect) ** 2 / expect).sum()
+    assert chi2 < 170.0, chi2  # 96 dof: p(chi2 > 170) ~ 5e-6
+    # fused k-hop in fast mode: structure must be self-consistent
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [8, 4], device=0, mode="GPU")
+    sampler.quiver.set_fast(True)
+    s_t = torch.from_numpy(seeds[:500])
+    n_id, bs, adjs = sampler.sample(s_t)
+    assert torch.equal(n_id[:bs].cpu(), s_t) and torch.unique(n_id).numel() == n_id.numel()
+    key = torch.from_numpy(np.repeat(np.arange(20000), np.diff(indptr)) * 20000 + indices).cuda().sort().values
+    n_dst = bs
+    deg = torch.from_numpy(np.diff(indptr)).cuda()
+    for adj, k in zip(adjs[::-1], [8, 4]):
+        src, dst = adj.edge_index
+        assert torch.equal(torch.bincount(dst, minlength=n_dst), deg[n_id[:n_dst]].clamp(max=k))
+        ekey = n_id[dst] * 20000 + n_id[src]
+        pos = torch.searchsorted(key, ekey).clamp(max=key.numel() - 1)
+        assert bool((key[pos] == ekey).all())
+        n_dst = int(adj.size[0])
+    assert n_dst == n_id.numel()

@@ -558,6 +558,91 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Opt-in fast sampling (qv_sampler_set_fast): NOT the reference's random stream.  Same contract -- min(deg, k) distinct
+// positions of the row, uniform, verbatim copy when deg <= k -- but position-independent and O(k) per row instead of
+// O(deg): the j-th pick of a row is perm(j), where perm is a keyed bijection of [0, deg) (a 4-round Feistel network on
+// ceil(log2 deg) bits, cycle-walked into range, keyed by (seed, call counter, node id)).  Distinctness holds by
+// construction, there are no generator states and no hub tails (a 142 k-degree row costs what a 40-degree row costs).
+// One output entry per thread.  Validated structurally and by a chi-square test, never against the reference's ids.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+__device__ __forceinline__ uint64_t feistel_pick(uint64_t j, uint64_t n, uint32_t k0, uint32_t k1)
+{
+    // bijection on [0, 2^(2h)) with 2^(2h) >= n, then cycle-walk back into [0, n)
+    int bits = 64 - __clzll(n - 1);
+    if (bits < 2) bits = 2;
+    const int h = (bits + 1) >> 1;
+    const uint64_t mask = (1ull << h) - 1;
+    uint64_t x = j;
+    do {
+        uint64_t l = x >> h, r = x & mask;
+#pragma unroll
+        for (int round = 0; round < 4; round++) {
+            const uint64_t f = mix32(static_cast<uint32_t>(r) ^ (k0 + 0x9E3779B9u * round)) ^
+                               (static_cast<uint64_t>(mix32(static_cast<uint32_t>(r >> 32) ^ k1 ^ round)) << 7);
+            const uint64_t nl = r;
+            r = (l ^ f) & mask;
+            l = nl;
+        }
+        x = (l << h) | r;
+    } while (x >= n);
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+    sample_rows_fast_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
+                            const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k_arg,
+                            const int64_t *__restrict__ out_ptr, const int64_t *__restrict__ d_E, uint32_t key0,
+                            uint32_t key1, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
+                            const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
+                            const int64_t *__restrict__ cached_deg)
+{
+    pdl_wait();
+    const int64_t S = dev_size(S_arg, d_S);
+    const int64_t E = *d_E;
+    const int64_t k = k_arg < 0 ? INT64_MAX : k_arg;
+    const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
+    for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < E;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        // owner row: largest r with out_ptr[r] <= e
+        int64_t lo = 0, hi = S;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (out_ptr[mid] <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int64_t r = lo, j = e - out_ptr[r];
+        int64_t start, deg, node = 0;
+        if (cached_deg) {
+            start = cached_start[r];
+            deg = cached_deg[r];
+            node = seeds[r];
+        } else {
+            node = seeds[r];
+            start = indptr[node];  // rows with entries are in range: count_scan gave out-of-range seeds 0 entries
+            deg = indptr[node + 1] - start;
+        }
+        const int64_t pos = deg <= k ? j
+                                     : static_cast<int64_t>(feistel_pick(static_cast<uint64_t>(j), static_cast<uint64_t>(deg),
+                                                                         key0 ^ mix32(static_cast<uint32_t>(node)),
+                                                                         key1 ^ static_cast<uint32_t>(node >> 32)));
+        out[e] = indices[start + pos];
+        if (row_out) row_out[row_off + e] = r;
+    }
+}
+
 template <bool kSlotsInSmem, bool kFast = true>
 __global__ void __launch_bounds__(kSampleWarps * 32)
     sample_rows_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
@@ -1002,6 +1087,8 @@ struct qv_sampler {
     Buffer fr_meta;   // [2][bound] int64: CSR row start / degree of every frontier node (fused k-hop path)
     Buffer node_map;  // MapWord per graph node: epoch-tagged first-occurrence map of the fused k-hop path
     unsigned int map_epoch = 0;  // 0 = the map has never been initialised
+    bool fast = false;           // opt-in non-reference sampling (qv_sampler_set_fast)
+    uint64_t fast_calls = 0;     // call counter mixed into the fast sampler's key
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
     unsigned int recip_n = 0;
     int64_t max_degree = 0;
@@ -1079,6 +1166,12 @@ int rng_states_for(qv_sampler *s, uint64_t rand_seed, int64_t rows_arg, const in
     return QV_OK;
 }
 
+inline unsigned grid_for(int64_t items, int threads, int n_sm, int waves = 8)
+{
+    const int64_t blocks = (items + threads - 1) / threads;
+    return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(n_sm) * waves)));
+}
+
 struct HopExtras {  // fused k-hop only; all null for the standalone calls
     const int64_t *cached_start = nullptr, *cached_deg = nullptr;
     MapWord *node_map = nullptr;
@@ -1102,10 +1195,21 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
 
 int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound, int64_t k,
                   uint64_t rand_seed, const int64_t *out_ptr, int64_t *out, int64_t *row_out, const int64_t *d_row_off,
-                  cudaStream_t st, const HopExtras &x = HopExtras(), bool *fused_insert = nullptr)
+                  cudaStream_t st, const HopExtras &x = HopExtras(), bool *fused_insert = nullptr,
+                  const int64_t *d_E = nullptr, int64_t E_bound = 0)
 {
     if (fused_insert) *fused_insert = false;
     if (S_bound <= 0) return QV_OK;
+    if (s->fast && d_E) {
+        if (E_bound <= 0) return QV_OK;
+        const uint64_t c = s->fast_calls++;
+        const uint64_t h = (rand_seed ^ (c * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+        QV_CUDA(launch_chained(sample_rows_fast_kernel, grid_for(E_bound, 256, s->n_sm), 256, 0, st, s->indptr, s->indices,
+                               s->n_nodes, seeds, S_arg, d_S, k, out_ptr, d_E, static_cast<uint32_t>(h),
+                               static_cast<uint32_t>(h >> 32), out, row_out, d_row_off, x.cached_start, x.cached_deg));
+        QV_CHECK_LAUNCH("sample_rows_fast_kernel");
+        return QV_OK;
+    }
     const uint32_t *states = nullptr;
     QV_TRY(rng_states_for(s, rand_seed, S_arg, d_S, S_bound, st, &states));
     const int64_t blocks = (S_bound + kSampleTile - 1) / kSampleTile;
@@ -1138,11 +1242,6 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     return QV_OK;
 }
 
-inline unsigned grid_for(int64_t items, int threads, int n_sm, int waves = 8)
-{
-    const int64_t blocks = (items + threads - 1) / threads;
-    return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(blocks, int64_t(n_sm) * waves)));
-}
 
 // clear + insert + frontier scan + emit, sizes from device scalars (or host args when the pointers are null)
 int launch_reindex(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
@@ -1292,8 +1391,10 @@ int qv_sample_fill(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, ui
     QV_REQUIRE(seeds && out_ptr, "qv_sample_fill: NULL array");
     QV_REQUIRE(k < (int64_t(1) << 31), "qv_sample_fill: fan-out %lld too large", (long long)k);
     DeviceGuard g(s->device);
+    // fast mode needs the total (left in d_meta by the qv_sample_count call that sized `neighbors`)
     return launch_sample(s, seeds, S, nullptr, S, k, rand_seed, out_ptr, neighbors, nullptr, nullptr,
-                         static_cast<cudaStream_t>(stream));
+                         static_cast<cudaStream_t>(stream), HopExtras(), nullptr, s->d_meta + kMetaE,
+                         s->fast ? s->h_meta[kMetaE] : 0);
 }
 
 int qv_reindex(qv_sampler *s, const int64_t *inputs, int64_t S, const int64_t *outputs, int64_t tot,
@@ -1410,7 +1511,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         if (bn[h] > fuse_below) xs.node_map = nullptr;
         // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
         QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st, xs,
-                             &fused_insert));
+                             &fused_insert, d_E, be[h]));
         if (!use_map) {
             QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
                                   nullptr, 2 * h + 1, st, d_next_S));
@@ -1498,6 +1599,13 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
         out_edges[h] = s->h_meta[kMetaStride * h + kMetaE];
         out_nodes[h + 1] = s->h_meta[kMetaStride * h + kMetaF];
     }
+    return QV_OK;
+}
+
+int qv_sampler_set_fast(qv_sampler *s, int enabled)
+{
+    QV_REQUIRE(s != nullptr, "qv_sampler_set_fast: NULL sampler");
+    s->fast = enabled != 0;
     return QV_OK;
 }
 

@@ -118,6 +118,11 @@ class Quiver:
         if registered_ptr:
             lib.qv_host_unregister(c_void_p(registered_ptr))
 
+    def set_fast(self, enabled=True):
+        """Extension: O(k)-per-row sampling that is NOT the reference's random stream (see qv_sampler_set_fast)."""
+        check(lib.qv_sampler_set_fast(self._handle, 1 if enabled else 0))
+        self.fast = bool(enabled)
+
     # -- Quiver.sample_neighbor(stream_num, vertices, k) ------------------------------------------------------------
     def sample_neighbor(self, stream_num, vertices, k):
         v = _check_long_cuda(vertices, "vertices", self.device)
