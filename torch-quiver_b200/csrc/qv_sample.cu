@@ -1,5 +1,6 @@
 // qv_sample.cu -- CSR k-hop neighbour sampler for B200 (sm_100a): count+scan, row-wise reservoir sampling with the
-// reference's exact XORWOW work decomposition, ordered-hash reindex, and the fused k-hop driver.
+// reference's exact XORWOW generator assignment, first-occurrence reindex (ordered hash table for the standalone call,
+// epoch-tagged direct node map inside a k-hop), the fused k-hop driver, cal_next, and an opt-in O(k) sampler.
 //
 // What it replaces (reference file:line):
 //   TorchQuiver::sample_neighbor / sample_kernel        srcs/cpp/src/quiver/cuda/quiver_sample.cu:113-200
@@ -17,7 +18,11 @@
 //   * prefix sums are single-pass chained scans (decoupled look-back) fused with the work that produces their input
 //     (degree/cap for the sampler, "is first occurrence" for the reindex);
 //   * XORWOW states come from a cache (qv_xorwow.cuh) instead of a per-thread skip-ahead every launch;
-//   * reservoir slots live in shared memory (32-bit), row metadata for a warp's 16 rows is fetched in one wave;
+//   * a lane walks its generator stream through its warp's 16 rows without any warp synchronisation (16 shared-memory
+//     reservoirs merged by atomicMax), `r mod m` comes from a fastmod reciprocal table instead of the XU pipe, and the
+//     ids to emit are one flat cp.async-staged list per warp;
+//   * inside a k-hop the frontier grows incrementally over a persistent node map whose words carry the call's epoch, so
+//     nothing is rebuilt or cleared per hop; the dependent kernels are chained with programmatic dependent launch;
 //   * int64 ids and 64-bit sizes throughout (the reference truncates to int in several places).
 #include <algorithm>
 #include <cstdlib>
