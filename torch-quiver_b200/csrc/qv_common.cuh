@@ -92,6 +92,41 @@ __device__ __forceinline__ void st_stream_v4(void *p, const int4 &v)
                  "r"(v.w)
                  : "memory");
 }
+// L2 eviction-priority variants: the gathered payload is touched once (evict_first), the small index / order arrays are
+// re-read by every call (evict_last), so the streaming rows do not push them out of the 126 MB L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_stream_v4_hint(const void *p, unsigned long long pol)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_stream_v4_hint(void *p, const int4 &v, unsigned long long pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ long long ld_keep_s64(const void *p, unsigned long long pol)
+{
+    long long r;
+    asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+    return r;
+}
+
 __device__ __forceinline__ int2 ld_stream_v2(const void *p)
 {
     int2 r;

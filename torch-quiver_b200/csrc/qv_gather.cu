@@ -223,8 +223,13 @@ __global__ void __launch_bounds__(256, kMinBlocks)
     const int64_t base = warp * 32;
     if (base >= n) return;
 
+    const unsigned long long pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     const char *my_src = nullptr;
-    if (base + lane < n) my_src = row_source(t, logical_row(indices, feature_order, n_rows_total, base + lane));
+    if (base + lane < n) {
+        long long id = indices[base + lane];
+        if (feature_order) id = (id >= 0 && id < n_rows_total) ? ld_keep_s64(feature_order + id, pol_keep) : -1;
+        my_src = row_source(t, id);
+    }
     const uint32_t rows_here = static_cast<uint32_t>(min(static_cast<int64_t>(32), n - base));
     const uint32_t total = rows_here * cpr;
     char *out_base = out + base * row_bytes;
@@ -247,12 +252,20 @@ __global__ void __launch_bounds__(256, kMinBlocks)
         typename L::T v[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; u++)
-            v[u] = (live[u] && src[u]) ? L::load(src[u] + static_cast<size_t>(col[u]) * kLoad) : L::zero();
+        {
+            if constexpr (kLoad == 16)
+                v[u] = (live[u] && src[u]) ? ld_stream_v4_hint(src[u] + static_cast<size_t>(col[u]) * kLoad, pol_stream)
+                                           : L::zero();
+            else
+                v[u] = (live[u] && src[u]) ? L::load(src[u] + static_cast<size_t>(col[u]) * kLoad) : L::zero();
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             if (live[u]) {
                 char *dst = out_base + off[u];
-                if constexpr (kLoad == kStore) {
+                if constexpr (kLoad == 16 && kStore == 16) {
+                    st_stream_v4_hint(dst, v[u], pol_stream);
+                } else if constexpr (kLoad == kStore) {
                     L::store(dst, v[u]);
                 } else {
                     static_assert(kLoad == 16 && kStore == 8, "only the 16/8 split is implemented");
