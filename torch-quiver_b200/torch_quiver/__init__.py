@@ -228,8 +228,13 @@ cpu_quiver_from_edge_index = cpu_quiver_from_csr_array
 _ELEMENT_DTYPE = {1: torch.uint8, 2: torch.float16, 4: torch.float32, 8: torch.float64}  # quiver_feature.cu:262-267
 
 
+import os as _os
+
+_PITCH_ALIGN = int(_os.environ.get("QUIVER_B200_PITCH_ALIGN", "16"))  # bytes; 64 aligns rows to DRAM access granules
+
+
 def _pitch_for(row_bytes):
-    return (row_bytes + 15) // 16 * 16
+    return (row_bytes + _PITCH_ALIGN - 1) // _PITCH_ALIGN * _PITCH_ALIGN
 
 
 class ShardTensorItem:
