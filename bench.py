@@ -293,6 +293,29 @@ def run_ours(args, rank, world, local_rank):
     else:
         total_ms, launches = serial_ms, launches_serial
 
+    # ---- timed region A': the same K steps through sample_and_gather (gather enqueued behind the last hop, frontier size
+    #      read on the device: no GPU idle while the host learns the sizes).  Same batches, same results (asserted). ------
+    fused_ms = None
+    if not args.no_fuse and not want_overlap:
+        fuse_target = feature if world == 1 else store
+        for b in batches_dev[:args.warmup]:
+            sampler.sample_and_gather(b, fuse_target)
+        launches0 = _lib.launch_count()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        edges_f = rows_f = 0
+        barrier()
+        a0.record()
+        for b in batches_dev[args.warmup:]:
+            n_id, _, adjs, res = sampler.sample_and_gather(b, fuse_target)
+            edges_f += sum(a.edge_index.shape[1] for a in adjs)
+            rows_f += res.shape[0]
+        a1.record()
+        barrier()
+        fused_ms = a0.elapsed_time(a1)
+        assert edges_f == edges and rows_f == rows  # same batches, same (deterministic) samples
+        assert torch.equal(res, feature[n_id])
+        total_ms, launches = fused_ms, _lib.launch_count() - launches0
+
     # ---- timed region B: end to end through the public API with HOST seeds -------------------------------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,6 +331,17 @@ def run_ours(args, rank, world, local_rank):
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    e2e_fused_ms = 0.0
+    if fused_ms is not None:  # informational: the same end-to-end loop through the fused extension call
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for b in batches_host[args.warmup:]:
+            n_id, _, adjs, res = sampler.sample_and_gather(b, fuse_target)
+            probe = res[-1, :1].cpu()
+        e1.record()
+        barrier()
+        e2e_fused_ms = e0.elapsed_time(e1)
     clock_summary = clocks.summary()
 
     # ---- roofline of the dominant kernel (the gather): back-to-back launches over the timed batches' node lists -------
@@ -336,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
     achieved = rows_per_launch * alg_bytes_per_row / (kern_ms * 1e-3) / 1e9
 
     # ---- reduce over ranks -------------------------------------------------------------------------------------------
-    stats = torch.tensor([total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms, e2e_fused_ms], dtype=torch.float64,
+                         device=dev)
     # ---- a large-batch point (64 k seeds): the sampler where bandwidth, not launch latency, matters -------
     big = None
     if not args.no_large_batch:
@@ -381,7 +416,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms = stats.tolist()
+    total_ms, sample_ms, gather_ms, e2e_ms, kern_ms, serial_ms, e2e_fused_ms = stats.tolist()
     edges_all, rows_all, e2e_edges_all, launches_all = sums.tolist()
     if rank != 0:
         return None
@@ -396,7 +431,10 @@ def run_ours(args, rank, world, local_rank):
                    "reference-exact XORWOW sampling (rand_seed 0)",
                    "pipelining": ("sampler on its own high-priority stream (as the reference's stream pool): sample(i+1) "
                                   "overlaps the still-running feature gather of step i; every call returns completed "
-                                  "results" if sampler.overlap else "none: sampler and gather on one stream"), "l2": "inputs larger than L2 (990 MB CSR + 980 MB "
+                                  "results" if sampler.overlap else
+                                  ("sample_and_gather (qv_khop_gather): the gather is enqueued behind the last hop with the "
+                                   "frontier size read on the device; one stream, one host wait per step"
+                                   if fused_ms is not None else "none: sampler and gather on one stream")), "l2": "inputs larger than L2 (990 MB CSR + 980 MB "
                    "feature table vs 126 MB L2); fresh seeds every step", "edges_per_step": edges_all / args.steps / world,
                    "rows_per_step": rows_all / args.steps / world},
         "seps_sampler_only": edges_all / (sample_ms * 1e-3),
@@ -411,7 +449,9 @@ def run_ours(args, rank, world, local_rank):
         "fast_mode": fast,
         "gpu_launches": int(launches_all),
         "e2e": {"value": e2e_edges_all / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": BATCH * 8,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                "api": "sampler.sample(host seeds) then feature[n_id] -- the reference's two calls",
+                "fused_value": (e2e_edges_all / (e2e_fused_ms * 1e-3)) if e2e_fused_ms > 0 else None},
         "clocks": clock_summary,
         "roofline": {"kernel": "gather_batch_flat_kernel<16,16> (feature gather, qv_gather.cu)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -459,6 +499,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-large-batch", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true",
+                    help="`value` from sample() + feature[n_id] as two calls instead of sample_and_gather")
     ap.add_argument("--overlap", action="store_true",
                     help="run the sampler on its own high-priority stream so sample(i+1) overlaps gather(i)")
     args = ap.parse_args()

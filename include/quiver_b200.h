@@ -180,6 +180,19 @@ QV_API int qv_khop_bounds(int64_t S, const int64_t *sizes, int n_hops, int64_t *
 QV_API int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
             int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream);
 
+/* sample -> gather without returning to the host in between (the two reference calls it replaces are
+ * GraphSageSampler.sample, sage_sampler.py:118-147, followed by Feature.__getitem__(n_id), feature.py:296-308).
+ * Same outputs as qv_khop, plus features[i, :] = row feature_order[n_id[i]] of `table` for i < out_nodes[n_hops]
+ * (qv_gather semantics; feature_order may be NULL).  The gather is enqueued BEHIND the sampling kernels with the
+ * frontier size read on the device, and the host wait covers only the sampler's sizes: the call returns while the
+ * gather may still be running on `stream` (stream-ordered like qv_gather).
+ *   features  [bound_nodes[n_hops] * row_bytes]   caller-allocated to the static bound; valid prefix out_nodes[n_hops] rows
+ * The table must be usable from the sampler's device. */
+QV_API int qv_khop_gather(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops,
+                   uint64_t rand_seed, int64_t *n_id, int64_t *const *edge_buf, const struct qv_shard_table *table,
+                   const int64_t *feature_order, int64_t row_bytes, void *features, int variant, int64_t *out_nodes,
+                   int64_t *out_edges, qv_stream_t stream);
+
 /* Quiver.cal_neighbor_prob(stream_num, last_prob, cur_prob, k) -- quiver_sample.cu:100-111 launching cal_next
  * (include/quiver/cuda_random.cu.hpp:71-104): one hop of access-probability propagation, fp32, same operation
  * order per node.  Asynchronous. */

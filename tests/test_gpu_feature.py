@@ -209,3 +209,77 @@ def test_reddit_scale_sample_then_tiered_gather():
     rows = feature[n_id]
     assert rows.shape == (n_id.numel(), D)
     assert torch.equal(rows.cpu(), x[n_id.cpu()])
+
+
+@pytest.mark.parametrize("policy,cache,d,dtype", [("device_replicate", "1G", 100, torch.float32),
+                                                  ("device_replicate", "2M", 100, torch.float32),
+                                                  ("device_replicate", 0, 128, torch.float16),
+                                                  ("p2p_clique_replicate", "1M", 602, torch.float32)])
+def test_sample_and_gather_equals_the_two_calls(oracle, policy, cache, d, dtype):
+    """the fused sample -> gather (qv_khop_gather, frontier size read on the device) returns exactly
+    what `sample(seeds)` followed by `feature[n_id]` returns -- ids vs the oracle k-hop, rows vs x[n_id], all tiers."""
+    import quiver
+    from graphs import powerlaw_csr
+    n = 40000
+    indptr, indices = powerlaw_csr(n, 12.0, seed=9)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    x = _mk(n, d, dtype, seed=5)
+    f = quiver.Feature(rank=0, device_list=[0], device_cache_size=cache, cache_policy=policy, csr_topo=topo)
+    f.from_cpu_tensor(x)
+    sampler = quiver.pyg.GraphSageSampler(topo, [7, 5, 3], device=0, mode="GPU")
+    for it, S in enumerate([1, 33, 1000, 257]):
+        seeds = torch.randperm(n, generator=torch.Generator().manual_seed(it))[:S].cuda()
+        n_id, bs, adjs, rows = sampler.sample_and_gather(seeds, f)
+        n_id2, bs2, adjs2 = sampler.sample(seeds)
+        assert bs == bs2 == S and torch.equal(n_id, n_id2) and len(adjs) == len(adjs2) == 3
+        for a, b in zip(adjs, adjs2):
+            assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.size, b.size)
+        want_nid = oracle.khop(indptr, indices, seeds.cpu().numpy(), [7, 5, 3])[0]
+        assert np.array_equal(n_id.cpu().numpy(), want_nid)
+        assert rows.shape == (n_id.numel(), d) and rows.dtype == dtype and rows.is_contiguous()
+        assert torch.equal(rows.cpu(), x[n_id.cpu()])
+        assert torch.equal(rows, f[n_id])
+
+
+def test_sample_and_gather_raw_shard_tensor_and_fallbacks():
+    """A bare ShardTensor (no feature_order), the empty batch and the "-1 = all neighbours" fan-out (no static bound:
+    the call falls back to the two separate calls) all give sample() + store[n_id]."""
+    import quiver
+    import torch_quiver as qv
+    from graphs import powerlaw_csr
+    n, d = 5000, 48
+    indptr, indices = powerlaw_csr(n, 6.0, seed=2)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    x = _mk(n, d, torch.float32, seed=1)
+    st = qv.ShardTensor(0)
+    st.append(x[:3000], 0)
+    st.append(x[3000:], -1)
+    seeds = torch.arange(0, 600, 3).cuda()
+    for sizes in ([4, 4], [3, -1]):
+        sampler = quiver.pyg.GraphSageSampler(topo, sizes, device=0, mode="GPU")
+        n_id, bs, adjs, rows = sampler.sample_and_gather(seeds, st)
+        n_id2, _, adjs2 = sampler.sample(seeds)
+        assert torch.equal(n_id, n_id2) and all(torch.equal(a.edge_index, b.edge_index) for a, b in zip(adjs, adjs2))
+        assert torch.equal(rows.cpu(), x[n_id.cpu()])
+    n_id, bs, adjs, rows = sampler.sample_and_gather(torch.empty(0, dtype=torch.long).cuda(), st)
+    assert bs == 0 and n_id.numel() == 0 and rows.shape[0] == 0
+
+
+def test_sample_and_gather_out_of_range_seed_takes_the_checked_path(oracle):
+    """An id outside [0, N) makes the direct node map bail out; the call is redone on the hash path and the gather with
+    it -- the result must still equal the per-call path (zero rows for the invalid id)."""
+    import quiver
+    from graphs import powerlaw_csr
+    n, d = 3000, 20
+    indptr, indices = powerlaw_csr(n, 5.0, seed=3)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    x = _mk(n, d, torch.float32, seed=2)
+    f = quiver.Feature(rank=0, device_list=[0], device_cache_size="1G", cache_policy="device_replicate")
+    f.from_cpu_tensor(x)
+    sampler = quiver.pyg.GraphSageSampler(topo, [3, 3], device=0, mode="GPU")
+    seeds = torch.tensor([5, n + 17, 9, 11]).cuda()
+    n_id, bs, adjs, rows = sampler.sample_and_gather(seeds, f)
+    n_id2, _, adjs2 = sampler.sample(seeds)
+    assert torch.equal(n_id, n_id2)
+    assert torch.equal(rows, f[n_id])
+    assert torch.count_nonzero(rows[1]) == 0

@@ -71,6 +71,9 @@ struct DeviceGuard {
 };
 
 int sm_count(int device);
+// qv_gather.cu: validate + enqueue a gather; d_n (optional) is a device-resident row count capped by the host bound n
+int gather_enqueue(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                   const int64_t *d_n, int64_t row_bytes, void *out, int variant, cudaStream_t st);
 
 // ---- device helpers ----
 constexpr int kWarp = 32;

@@ -53,6 +53,15 @@ __device__ __forceinline__ int64_t logical_row(const int64_t *__restrict__ indic
     return id;
 }
 
+// Number of rows to gather: `n` from the host, capped by a device-resident count when the caller does not know the
+// size on the host yet (qv_khop_gather: the frontier size is still being computed when the gather is enqueued; `n` is
+// then the static bound the grid was sized for).
+__device__ __forceinline__ int64_t live_rows(int64_t n, const int64_t *__restrict__ d_n)
+{
+    if (d_n) n = min(n, max(static_cast<int64_t>(0), *d_n));
+    return n;
+}
+
 template <int kBytes>
 struct Chunk;
 template <>
@@ -102,11 +111,12 @@ constexpr int kGatherUnroll = 4;
 template <int kBytes>
 __global__ void __launch_bounds__(kGatherThreads)
     gather_flat_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
-                       const int64_t *__restrict__ feature_order, int64_t n, uint32_t cpr, uint32_t inv,
-                       char *__restrict__ out)
+                       const int64_t *__restrict__ feature_order, int64_t n, const int64_t *__restrict__ d_n,
+                       uint32_t cpr, uint32_t inv, char *__restrict__ out)
 {
     using C = Chunk<kBytes>;
     constexpr uint32_t kTile = kGatherThreads * kGatherUnroll;
+    n = live_rows(n, d_n);
     const int64_t total_chunks = n * static_cast<int64_t>(cpr);
     const int64_t tile_base = static_cast<int64_t>(blockIdx.x) * kTile;
     // first row of the tile and the tile's chunk offset inside that row (one 64-bit division per thread)
@@ -159,10 +169,12 @@ constexpr int kBatchUnroll = 4;
 template <int kLoad, int kStore, int kGroup>
 __global__ void __launch_bounds__(256)
     gather_batch_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
-                        const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, char *__restrict__ out)
+                        const int64_t *__restrict__ feature_order, int64_t n, const int64_t *__restrict__ d_n,
+                        uint32_t row_bytes, char *__restrict__ out)
 {
     using L = Chunk<kLoad>;
     constexpr int kRowsPerIter = 32 / kGroup;
+    n = live_rows(n, d_n);
     const int lane = threadIdx.x & 31;
     const int sub = lane % kGroup, grp = lane / kGroup;
     const int64_t n_rows_total = t.row_begin[t.n_shards];
@@ -213,11 +225,12 @@ __global__ void __launch_bounds__(256)
 template <int kLoad, int kStore, int kUnroll = kBatchUnroll, int kMinBlocks = 5>
 __global__ void __launch_bounds__(256, kMinBlocks)
     gather_batch_flat_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
-                             const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, uint32_t cpr,
-                             uint32_t inv, char *__restrict__ out)
+                             const int64_t *__restrict__ feature_order, int64_t n, const int64_t *__restrict__ d_n,
+                             uint32_t row_bytes, uint32_t cpr, uint32_t inv, char *__restrict__ out)
 {
     using L = Chunk<kLoad>;
     const int lane = threadIdx.x & 31;
+    n = live_rows(n, d_n);
     const int64_t n_rows_total = t.row_begin[t.n_shards];
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t base = warp * 32;
@@ -281,9 +294,11 @@ __global__ void __launch_bounds__(256, kMinBlocks)
 template <int kBytes>
 __global__ void __launch_bounds__(256)
     gather_rows_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
-                       const int64_t *__restrict__ feature_order, int64_t n, int64_t cpr, char *__restrict__ out)
+                       const int64_t *__restrict__ feature_order, int64_t n, const int64_t *__restrict__ d_n,
+                       int64_t cpr, char *__restrict__ out)
 {
     using C = Chunk<kBytes>;
+    n = live_rows(n, d_n);
     const int64_t n_rows_total = t.row_begin[t.n_shards];
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -349,10 +364,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __global__ void __launch_bounds__(32)
     gather_tma_kernel(const __grid_constant__ GatherParams t, const int64_t *__restrict__ indices,
-                      const int64_t *__restrict__ feature_order, int64_t n, uint32_t row_bytes, int rows_per_stage,
-                      char *__restrict__ out)
+                      const int64_t *__restrict__ feature_order, int64_t n, const int64_t *__restrict__ d_n,
+                      uint32_t row_bytes, int rows_per_stage, char *__restrict__ out)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    n = live_rows(n, d_n);
     __shared__ __align__(8) uint64_t full[kTmaStages];
     const int lane = threadIdx.x;
     const uint32_t stage_bytes = row_bytes * rows_per_stage;
@@ -446,7 +462,7 @@ inline int pick_chunk(int64_t row_bytes, const qv_shard_table *tab, const void *
 
 template <int kLoad, int kStore>
 int launch_batch(const GatherParams &p, const int64_t *indices, const int64_t *feature_order, int64_t n,
-                 int64_t row_bytes, char *out, cudaStream_t st)
+                 const int64_t *d_n, int64_t row_bytes, char *out, cudaStream_t st)
 {
     const int64_t cpr = (row_bytes + kLoad - 1) / kLoad;
     const int64_t warps = (n + 31) / 32;
@@ -459,13 +475,13 @@ int launch_batch(const GatherParams &p, const int64_t *indices, const int64_t *f
         const uint32_t inv = static_cast<uint32_t>((uint64_t(1) << 32) / static_cast<uint64_t>(cpr)) + 1u;
         // (rows in flight per lane, min blocks per SM) = (4, 5): a sweep over {2,4,8} x {3..8} stayed within 0.75-0.79
         // of the HBM peak on 400-byte rows -- the kernel sits on the DRAM random-access limit, not on occupancy
-        gather_batch_flat_kernel<kLoad, kStore><<<g, 256, 0, st>>>(p, indices, feature_order, n, rb,
+        gather_batch_flat_kernel<kLoad, kStore><<<g, 256, 0, st>>>(p, indices, feature_order, n, d_n, rb,
                                                                     static_cast<uint32_t>(cpr), inv, out);
         QV_CHECK_LAUNCH("gather_batch_flat_kernel");
         return QV_OK;
     }
 #define QV_LAUNCH_GROUP(G)                                                                                     \
-    gather_batch_kernel<kLoad, kStore, G><<<g, 256, 0, st>>>(p, indices, feature_order, n, rb, out)
+    gather_batch_kernel<kLoad, kStore, G><<<g, 256, 0, st>>>(p, indices, feature_order, n, d_n, rb, out)
     if (cpr > 16)
         QV_LAUNCH_GROUP(32);
     else if (cpr > 8)
@@ -485,7 +501,7 @@ int launch_batch(const GatherParams &p, const int64_t *indices, const int64_t *f
 
 template <int kBytes>
 int launch_simt(const GatherParams &p, const int64_t *indices, const int64_t *feature_order, int64_t n,
-                int64_t row_bytes, char *out, int n_sm, cudaStream_t st)
+                const int64_t *d_n, int64_t row_bytes, char *out, int n_sm, cudaStream_t st)
 {
     const int64_t cpr = row_bytes / kBytes;
     constexpr int64_t kTile = kGatherThreads * kGatherUnroll;
@@ -495,22 +511,20 @@ int launch_simt(const GatherParams &p, const int64_t *indices, const int64_t *fe
     if ((cpr + kTile) * cpr < (int64_t(1) << 32) && blocks < (int64_t(1) << 31)) {
         const uint32_t inv = static_cast<uint32_t>((uint64_t(1) << 32) / static_cast<uint64_t>(cpr)) + 1u;
         gather_flat_kernel<kBytes><<<static_cast<unsigned>(blocks), kGatherThreads, 0, st>>>(
-            p, indices, feature_order, n, static_cast<uint32_t>(cpr), cpr == 1 ? 0u : inv, out);
+            p, indices, feature_order, n, d_n, static_cast<uint32_t>(cpr), cpr == 1 ? 0u : inv, out);
         QV_CHECK_LAUNCH("gather_flat_kernel");
     } else {
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, int64_t(n_sm) * 16));
-        gather_rows_kernel<kBytes><<<grid, 256, 0, st>>>(p, indices, feature_order, n, cpr, out);
+        gather_rows_kernel<kBytes><<<grid, 256, 0, st>>>(p, indices, feature_order, n, d_n, cpr, out);
         QV_CHECK_LAUNCH("gather_rows_kernel");
     }
     return QV_OK;
 }
 }  // namespace
-}  // namespace qv
 
-using namespace qv;
-
-extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
-                         int64_t row_bytes, void *out, int variant, qv_stream_t stream)
+// Validates the request and enqueues the gather.  d_n (optional) = device-resident row count, n = its host-side bound.
+int gather_enqueue(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                   const int64_t *d_n, int64_t row_bytes, void *out, int variant, cudaStream_t st)
 {
     QV_REQUIRE(table != nullptr, "qv_gather: table is NULL");
     QV_REQUIRE(table->n_shards >= 1 && table->n_shards <= QV_MAX_SHARDS, "qv_gather: n_shards = %d outside [1, %d]",
@@ -538,7 +552,6 @@ extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, co
     int device = 0;
     QV_CUDA(cudaGetDevice(&device));
     const int n_sm = sm_count(device);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     char *o = static_cast<char *>(out);
     const int chunk = pick_chunk(row_bytes, table, out);
 
@@ -559,7 +572,7 @@ extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, co
         const int64_t n_groups = (n + rows_per_stage - 1) / rows_per_stage;
         const int ctas_per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem + 1024))));
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>(n_groups, int64_t(n_sm) * ctas_per_sm));
-        gather_tma_kernel<<<grid, 32, smem, st>>>(p, indices, feature_order, n, static_cast<uint32_t>(row_bytes),
+        gather_tma_kernel<<<grid, 32, smem, st>>>(p, indices, feature_order, n, d_n, static_cast<uint32_t>(row_bytes),
                                                    rows_per_stage, o);
         QV_CHECK_LAUNCH("gather_tma_kernel");
         return QV_OK;
@@ -573,28 +586,38 @@ extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, co
                 src16 = false;
         switch (chunk) {
         case 16:
-            return launch_batch<16, 16>(p, indices, feature_order, n, row_bytes, o, st);
+            return launch_batch<16, 16>(p, indices, feature_order, n, d_n, row_bytes, o, st);
         case 8:
-            if (src16) return launch_batch<16, 8>(p, indices, feature_order, n, row_bytes, o, st);
-            return launch_batch<8, 8>(p, indices, feature_order, n, row_bytes, o, st);
+            if (src16) return launch_batch<16, 8>(p, indices, feature_order, n, d_n, row_bytes, o, st);
+            return launch_batch<8, 8>(p, indices, feature_order, n, d_n, row_bytes, o, st);
         case 4:
-            return launch_batch<4, 4>(p, indices, feature_order, n, row_bytes, o, st);
+            return launch_batch<4, 4>(p, indices, feature_order, n, d_n, row_bytes, o, st);
         case 2:
-            return launch_batch<2, 2>(p, indices, feature_order, n, row_bytes, o, st);
+            return launch_batch<2, 2>(p, indices, feature_order, n, d_n, row_bytes, o, st);
         default:
-            return launch_batch<1, 1>(p, indices, feature_order, n, row_bytes, o, st);
+            return launch_batch<1, 1>(p, indices, feature_order, n, d_n, row_bytes, o, st);
         }
     }
     switch (chunk) {
     case 16:
-        return launch_simt<16>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+        return launch_simt<16>(p, indices, feature_order, n, d_n, row_bytes, o, n_sm, st);
     case 8:
-        return launch_simt<8>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+        return launch_simt<8>(p, indices, feature_order, n, d_n, row_bytes, o, n_sm, st);
     case 4:
-        return launch_simt<4>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+        return launch_simt<4>(p, indices, feature_order, n, d_n, row_bytes, o, n_sm, st);
     case 2:
-        return launch_simt<2>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+        return launch_simt<2>(p, indices, feature_order, n, d_n, row_bytes, o, n_sm, st);
     default:
-        return launch_simt<1>(p, indices, feature_order, n, row_bytes, o, n_sm, st);
+        return launch_simt<1>(p, indices, feature_order, n, d_n, row_bytes, o, n_sm, st);
     }
+}
+}  // namespace qv
+
+using namespace qv;
+
+extern "C" int qv_gather(const qv_shard_table *table, const int64_t *indices, const int64_t *feature_order, int64_t n,
+                         int64_t row_bytes, void *out, int variant, qv_stream_t stream)
+{
+    return gather_enqueue(table, indices, feature_order, n, nullptr, row_bytes, out, variant,
+                          static_cast<cudaStream_t>(stream));
 }

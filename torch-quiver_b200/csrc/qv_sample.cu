@@ -1456,10 +1456,19 @@ namespace
 {
 constexpr int kMetaErr = kMetaStride * QV_MAX_HOPS + 3;  // a free device scalar: "id outside [0, n_nodes) seen"
 
+// Feature gather to enqueue behind the last hop (qv_khop_gather); table == nullptr: none.
+struct GatherTail {
+    const qv_shard_table *table = nullptr;
+    const int64_t *feature_order = nullptr;
+    int64_t row_bytes = 0;
+    void *features = nullptr;
+    int variant = 0;
+};
+
 // One attempt of the fused k-hop.  use_map: direct node map (default) or the per-hop hash table.
 int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
              int64_t *n_id, int64_t *const *edge_buf, const int64_t *bn, const int64_t *be, bool use_map, cudaStream_t st,
-             bool *id_error)
+             bool *id_error, const GatherTail &tail)
 {
     int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
     int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
@@ -1552,14 +1561,53 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
     }
     QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     QV_CUDA(cudaEventRecord(s->meta_ready, st));
+    if (tail.table) {
+        // The sizes are already on their way to the host; the gather goes in behind them with the frontier size read on
+        // the device (grid sized for the static bound), so the host wakes up -- and the caller builds its tensors --
+        // while the rows are being copied.  After an id error n_id holds arbitrary values: the gather range-checks every
+        // id (zero rows), and the whole call is redone by the caller.
+        const int64_t *d_n = s->d_meta + kMetaStride * (n_hops - 1) + kMetaF;
+        QV_TRY(gather_enqueue(tail.table, n_id, tail.feature_order, bn[n_hops], d_n, tail.row_bytes, tail.features,
+                              tail.variant, st));
+    }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
     if (use_map && s->h_meta[kMetaErr] != 0) *id_error = true;  // the caller redoes the call on the hash path
     return QV_OK;
 }
+
+int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+               int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream,
+               const GatherTail &tail);
 }  // namespace
 
 int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
             int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream)
+{
+    return khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, out_nodes, out_edges, stream, GatherTail());
+}
+
+int qv_khop_gather(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+                   int64_t *n_id, int64_t *const *edge_buf, const qv_shard_table *table, const int64_t *feature_order,
+                   int64_t row_bytes, void *features, int variant, int64_t *out_nodes, int64_t *out_edges,
+                   qv_stream_t stream)
+{
+    QV_REQUIRE(table != nullptr, "qv_khop_gather: table is NULL");
+    QV_REQUIRE(features != nullptr || S == 0, "qv_khop_gather: features is NULL");
+    QV_REQUIRE(row_bytes > 0, "qv_khop_gather: row_bytes = %lld", (long long)row_bytes);
+    GatherTail tail;
+    tail.table = table;
+    tail.feature_order = feature_order;
+    tail.row_bytes = row_bytes;
+    tail.features = features;
+    tail.variant = variant;
+    return khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, out_nodes, out_edges, stream, tail);
+}
+
+namespace
+{
+int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+               int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream,
+               const GatherTail &tail)
 {
     QV_REQUIRE(s && sizes && out_nodes && out_edges, "qv_khop: NULL argument");
     int64_t bn[QV_MAX_HOPS + 1], be[QV_MAX_HOPS];
@@ -1595,10 +1643,10 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
         s->fr_meta.release();
 
     bool id_error = false;
-    QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, use_map, st, &id_error));
+    QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, use_map, st, &id_error, tail));
     if (id_error) {
         QV_TRY(ensure_table(s, bn[n_hops]));
-        QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, false, st, &id_error));
+        QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, false, st, &id_error, tail));
     }
     for (int h = 0; h < n_hops; h++) {
         out_edges[h] = s->h_meta[kMetaStride * h + kMetaE];
@@ -1606,6 +1654,7 @@ int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes
     }
     return QV_OK;
 }
+}  // namespace
 
 int qv_sampler_set_fast(qv_sampler *s, int enabled)
 {

@@ -29,6 +29,26 @@ class _FakeDevice(object):
 _EMPTY_E_ID = torch.tensor([])
 
 
+def _fusable_store(feature, device):
+    """(torch_quiver.ShardTensor, feature_order) when `feature[n_id]` is a single qv_gather on `device`, else (None, None)."""
+    order = None
+    store = feature
+    if hasattr(feature, "_my_store"):  # quiver.Feature
+        if getattr(feature, "ipc_handle_", None) is not None:
+            feature.lazy_init_from_ipc_handle()
+        if feature.rank != device:
+            return None, None
+        order = feature.feature_order
+        store = feature._my_store()
+    if hasattr(store, "_other_clique_devices"):  # quiver.shard_tensor.ShardTensor
+        if store.current_device != device or store._other_clique_devices():
+            return None, None
+        store = store.shard_tensor
+    if not isinstance(store, qv.ShardTensor) or not store.shards:
+        return None, None
+    return store, order
+
+
 class GraphSageSampler:
     r"""Behaves like PyG's `NeighborSampler`: `sample(seeds)` returns `(n_id, batch_size, adjs)` with `adjs` ordered
     outermost hop first, `adj.edge_index[0]` indexing into `n_id` (sources) and `edge_index[1]` into the hop's targets.
@@ -121,6 +141,33 @@ class GraphSageSampler:
             adjs.append(Adj(edge_index, torch.tensor([]), torch.LongTensor([frontier.size(0), nodes.size(0)])))
             nodes = frontier
         return nodes, batch_size, adjs[::-1]
+
+    def sample_and_gather(self, input_nodes, feature):
+        """Extension: `n_id, bs, adjs = sample(seeds); x = feature[n_id]` as ONE device pipeline.
+
+        The feature rows of n_id are gathered right behind the last hop with the frontier size read on the device, so
+        the GPU does not idle while the host learns the sizes and builds the Adj list.  Returns
+        (n_id, batch_size, adjs, x), element-wise identical to the two separate calls.  `feature` is a quiver.Feature
+        or a quiver.shard_tensor.ShardTensor bound to this sampler's device; when the fused path does not apply (rows in
+        another P2P clique, negative fan-out, empty batch, per-hop mode) the two calls are made one after the other."""
+        self.lazy_init_quiver()
+        if not isinstance(input_nodes, torch.Tensor):
+            input_nodes = torch.tensor(input_nodes)
+        batch_size = len(input_nodes)
+        store, order = _fusable_store(feature, self.device)
+        if (store is not None and self.fused and not self.overlap and batch_size > 0 and all(s >= 0 for s in self.sizes)
+                and torch.cuda.current_device() == self.device):
+            try:
+                n_id, hops, x = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes,
+                                                        gather=(store, order))
+            except qv.Unsupported:
+                pass
+            else:
+                sizes = torch.tensor([[n_src, n_dst] for _, n_src, n_dst in hops], dtype=torch.long)
+                adjs = [Adj(hop[0], _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
+                return n_id, batch_size, adjs[::-1], x
+        n_id, batch_size, adjs = self.sample(input_nodes)
+        return n_id, batch_size, adjs, feature[n_id]
 
     def _sample_khop_overlapped(self, input_nodes):
         if self._priv_stream is None:

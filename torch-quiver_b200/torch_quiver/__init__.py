@@ -167,12 +167,16 @@ class Quiver:
                                        _stream(self.device)))
 
     # -- fused k-hop (ours): every hop enqueued back to back, one host synchronisation --------------------------------
-    def sample_khop(self, seeds, sizes):
+    def sample_khop(self, seeds, sizes, gather=None):
         """All hops of GraphSageSampler.sample (sage_sampler.py:118-147) in one C call.
 
         Returns (n_id, [(edge_index[2, E_l], n_src_l, n_dst_l) for l in hops, innermost first]).
         Raises `Unsupported` when a size is negative or the static bound is too large (callers fall back to the
-        per-hop calls)."""
+        per-hop calls).
+
+        gather=(shard_tensor, feature_order or None): also gather the feature rows of n_id behind the last hop, without
+        a host round trip in between (qv_khop_gather); returns (n_id, hops, x) with x = shard_tensor[feature_order[n_id]]
+        produced stream-ordered on the current stream.  x is a view of a buffer sized for the static frontier bound."""
         v = _check_long_cuda(seeds, "seeds", self.device)
         n_hops = len(sizes)
         S = v.numel()
@@ -199,13 +203,29 @@ class Quiver:
         base = arena.data_ptr()
         for h in range(n_hops):
             buf_ptrs[h] = base + 8 * offs[h]
-        check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs, out_nodes,
-                          out_edges, _stream(self.device)))
+        x = None
+        if gather is None:
+            check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs,
+                              out_nodes, out_edges, _stream(self.device)))
+        else:
+            store, feature_order = gather
+            if torch.cuda.current_device() != self.device:
+                raise RuntimeError("sample_khop(gather=...) must run with the sampler's device current")
+            table, dtype, row_shape, row_bytes = store._gather_plan(self.device)
+            order_ptr = c_void_p(0)
+            if feature_order is not None:
+                order_ptr = _ptr(_check_long_cuda(feature_order, "feature_order", self.device))
+            x = torch.empty([max(n_id_cap, 1)] + row_shape, dtype=dtype, device=v.device)
+            check(lib.qv_khop_gather(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs,
+                                     byref(table), order_ptr, row_bytes, _ptr(x), int(store.gather_variant), out_nodes,
+                                     out_edges, _stream(self.device)))
         hops = []
         for h in range(n_hops):
             E = out_edges[h]
             hops.append((arena[offs[h]:offs[h] + 2 * E].view(2, E), out_nodes[h + 1], out_nodes[h]))
-        return arena[:out_nodes[n_hops]], hops
+        if gather is None:
+            return arena[:out_nodes[n_hops]], hops
+        return arena[:out_nodes[n_hops]], hops, x[:out_nodes[n_hops]]
 
 
 def device_quiver_from_csr_array(indptr, indices, edge_ids=None, device=0, cuda=False):
@@ -377,27 +397,30 @@ class ShardTensor:
         t.row_begin[len(self.shards)] = self.offset_list_[-1]
         return t
 
-    def gather(self, indices, feature_order=None, out=None):
-        """`self[indices]` with the optional `feature_order[idx]` indirection folded into the kernel."""
+    def _gather_plan(self, current):
+        """(shard table as seen from device `current`, dtype, row shape, row bytes) -- cached per device."""
         if not self.shards:
             raise RuntimeError("ShardTensor is empty")
-        idx = _check_long_cuda(indices, "indices")
-        current = idx.device.index
-        n = idx.numel()
         dtype = self.dtype or _ELEMENT_DTYPE.get(self.element_size)
         if dtype is None:
             raise RuntimeError(f"unsupported element size {self.element_size}")
+        cache = getattr(self, "_table_cache", None)
+        if cache is None or cache[0] != (current, len(self.shards)):
+            self._table_cache = ((current, len(self.shards)), self._table(current))
+        return self._table_cache[1], dtype, list(self.shape_[1:]), self._row_bytes()
+
+    def gather(self, indices, feature_order=None, out=None):
+        """`self[indices]` with the optional `feature_order[idx]` indirection folded into the kernel."""
+        idx = _check_long_cuda(indices, "indices")
+        current = idx.device.index
+        n = idx.numel()
+        table, dtype, row_shape, _ = self._gather_plan(current)
         if out is None:
-            out = torch.empty([n] + self.shape_[1:], dtype=dtype, device=idx.device)
+            out = torch.empty([n] + row_shape, dtype=dtype, device=idx.device)
         order_ptr = c_void_p(0)
         if feature_order is not None:
             fo = _check_long_cuda(feature_order, "feature_order", current)
             order_ptr = _ptr(fo)
-        key = current
-        cache = getattr(self, "_table_cache", None)
-        if cache is None or cache[0] != (key, len(self.shards)):
-            self._table_cache = ((key, len(self.shards)), self._table(current))
-        table = self._table_cache[1]
         if torch.cuda.current_device() == current:
             check(lib.qv_gather(byref(table), _ptr(idx), order_ptr, n, self._row_bytes(), _ptr(out),
                                 int(self.gather_variant), _stream(current)))

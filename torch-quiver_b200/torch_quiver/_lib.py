@@ -66,6 +66,9 @@ PROTOTYPES = {
     "qv_khop_bounds": (c_int, [c_int64, POINTER(c_int64), c_int, POINTER(c_int64), POINTER(c_int64)]),
     "qv_khop": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_uint64, c_void_p, POINTER(c_void_p),
                         POINTER(c_int64), POINTER(c_int64), c_void_p]),
+    "qv_khop_gather": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_uint64, c_void_p, POINTER(c_void_p),
+                               POINTER(ShardTable), c_void_p, c_int64, c_void_p, c_int, POINTER(c_int64),
+                               POINTER(c_int64), c_void_p]),
     "qv_sampler_set_fast": (c_int, [c_void_p, c_int]),
     "qv_cal_neighbor_prob": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
 }
