@@ -19,6 +19,33 @@ def powerlaw_csr(n_nodes, mean_deg, seed=0, alpha=2.0, max_deg=None, zero_frac=0
     return indptr, indices[order]
 
 
+def rmat_csr(scale, n_edges, n_nodes=None, abcd=(0.57, 0.19, 0.19, 0.05), seed=2, dedup=False):
+    """BASELINE config 2 shape: R-MAT edges with (a,b,c,d) = (0.57,0.19,0.19,0.05) over 2^scale ids,
+    trimmed to `n_nodes`; duplicates kept unless `dedup` (a multigraph row is legal CSR input: sampling is by POSITION).
+    Heavy skew, many empty rows, duplicate neighbours -- a different degree structure from the pareto graphs."""
+    rng = np.random.default_rng(seed)
+    a, b, c, _ = abcd
+    src = np.zeros(n_edges, np.int64)
+    dst = np.zeros(n_edges, np.int64)
+    for _level in range(scale):
+        r = rng.random(n_edges)
+        down = r >= a + b  # quadrants c, d: lower half (src bit set)
+        right = ((r >= a) & (r < a + b)) | (r >= a + b + c)  # quadrants b, d: right half (dst bit set)
+        src = (src << 1) | down
+        dst = (dst << 1) | right
+    n = n_nodes if n_nodes is not None else (1 << scale)
+    keep = (src < n) & (dst < n)
+    src, dst = src[keep], dst[keep]
+    if dedup:
+        key = np.unique(src * n + dst)
+        src, dst = key // n, key % n
+    order = np.lexsort((dst, src))
+    src, dst = src[order], dst[order]
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(np.bincount(src, minlength=n), out=indptr[1:])
+    return indptr, dst
+
+
 def simple_graph(n, nbr):
     """The reference's own sampler fixture: node i has neighbours (j+1)*n + i (tests/cpp/test_quiver_cpu.cpp:9-30).
     Neighbour ids exceed n, so the CSR is padded with empty rows up to the largest id."""

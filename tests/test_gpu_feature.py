@@ -283,3 +283,35 @@ def test_sample_and_gather_out_of_range_seed_takes_the_checked_path(oracle):
     assert torch.equal(n_id, n_id2)
     assert torch.equal(rows, f[n_id])
     assert torch.count_nonzero(rows[1]) == 0
+
+
+def test_from_mmap_with_id_parts_and_saved_parts(tmp_path):
+    """Feature.from_mmap (feature.py:95-192): parts given as row-id tensors into a numpy memmap, or as paths of saved row
+    tensors (the `.pth` layout quiver_partition_feature writes, partition.py:234-247); set_local_order restores original
+    ids (feature.py:283-294)."""
+    import quiver
+    from quiver.feature import DeviceConfig
+    n, d = 20000, 64
+    path = tmp_path / "feat.bin"
+    arr = np.memmap(path, dtype=np.float32, mode="w+", shape=(n, d))
+    arr[:] = np.random.default_rng(3).integers(0, 10, (n, d)).astype(np.float32)
+    arr.flush()
+    mm = np.memmap(path, dtype=np.float32, mode="r", shape=(n, d))
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(0))
+    hot, cold = perm[:6000], perm[6000:]
+    idx = torch.randint(0, n, (50000, ))
+    full = torch.from_numpy(np.array(mm))  # a writable copy
+    want = full[idx]
+
+    f = quiver.Feature(rank=0, device_list=[0], device_cache_size=0, cache_policy="device_replicate")
+    f.from_mmap(mm, DeviceConfig([hot], cold))
+    f.set_local_order(perm)
+    assert f.shape == [n, d]
+    assert torch.equal(f[idx.cuda()].cpu(), want)
+
+    torch.save(full[hot].clone(), tmp_path / "gpu0.pth")
+    torch.save(full[cold].clone(), tmp_path / "cpu.pth")
+    g = quiver.Feature(rank=0, device_list=[0], device_cache_size=0, cache_policy="device_replicate")
+    g.from_mmap(None, DeviceConfig([str(tmp_path / "gpu0.pth")], str(tmp_path / "cpu.pth")))
+    g.set_local_order(perm)
+    assert torch.equal(g[idx.cuda()].cpu(), want)

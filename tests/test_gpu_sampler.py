@@ -406,3 +406,93 @@ def test_fast_mode_is_valid_uniform_and_not_the_reference_stream(oracle):
         assert bool((key[pos] == ekey).all())
         n_dst = int(adj.size[0])
     assert n_dst == n_id.numel()
+
+
+def _compact_rows(indptr, indices, rows):
+    """CSR of just `rows` (row i of the result = rows[i]): sampling depends on a row's position in the seed list, its
+    degree and its contents -- not on where the row lives -- so the oracle can be run on this instead of a multi-GB CSR."""
+    start = indptr[rows]
+    deg = indptr[rows + 1] - start
+    cptr = torch.zeros(rows.numel() + 1, dtype=torch.long, device=rows.device)
+    cptr[1:] = deg.cumsum(0)
+    tot = int(cptr[-1])
+    src = torch.repeat_interleave(start - cptr[:-1], deg) + torch.arange(tot, device=rows.device)
+    return cptr.cpu().numpy(), indices[src].cpu().numpy()
+
+
+def test_more_than_2_31_edges_bit_exact(oracle):
+    """Maximum sizes: a CSR with 2.2e9 edges (17.6 GB of int64 ids, papers100M-symmetrised scale).  Every row offset past
+    edge 2^31 needs 64-bit arithmetic end to end (the reference's thrust path carries int offsets in places).
+    Sampled ids are compared bit for bit with the oracle run on the compacted rows of the seeds; the fused k-hop is
+    compared with the per-hop calls and checked for membership."""
+    import torch_quiver as qv
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~40 GB of free HBM")
+    N = 4_000_000
+    deg = torch.where(torch.arange(N, device="cuda") % 2 == 0, 5, 1095)  # copy path and reservoir path, mean 550
+    indptr = torch.zeros(N + 1, dtype=torch.long, device="cuda")
+    indptr[1:] = deg.cumsum(0)
+    E = int(indptr[-1])
+    assert E > 2**31
+    indices = torch.empty(E, dtype=torch.long, device="cuda")
+    step = 1 << 27
+    for lo in range(0, E, step):  # ids from a formula, filled in place chunk by chunk
+        e = torch.arange(lo, min(lo + step, E), device="cuda")
+        indices[lo:lo + step] = (e * 2654435761 + (e >> 9)) % N
+    del e
+    q = qv.device_quiver_from_csr_array(indptr, indices, None, 0, True)
+    rows = torch.cat([N - 1 - torch.arange(0, 3000, device="cuda") * 7,          # offsets around 2.2e9
+                      int(N * 0.977) + torch.arange(0, 900, device="cuda"),  # just past 2^31
+                      torch.arange(0, 500, device="cuda") * 11])                   # and the low end
+    assert int(indptr[rows].max()) > 2**31
+    cptr, cidx = _compact_rows(indptr, indices, rows)
+    local = np.arange(rows.numel(), dtype=np.int64)
+    for k in (3, 15, 40):
+        out, cnt = q.sample_neighbor(0, rows, k)
+        o_out, o_cnt = oracle.sample_neighbor(cptr, cidx, local, k)
+        assert np.array_equal(cnt.cpu().numpy(), o_cnt) and np.array_equal(out.cpu().numpy(), o_out), k
+    # fused k-hop == per-hop calls, and every edge is an edge of the graph
+    nodes, hops_ref = rows, []
+    for k in (15, 10):
+        out, cnt = q.sample_neighbor(0, nodes, k)
+        frontier, row_idx, col_idx = q.reindex_single(nodes, out, cnt)
+        hops_ref.append(torch.stack([col_idx, row_idx]))
+        nodes = frontier
+    n_id, hops = q.sample_khop(rows, [15, 10])
+    assert torch.equal(n_id, nodes)
+    for (ei, n_src, n_dst), want in zip(hops, hops_ref):
+        assert torch.equal(ei, want)
+        tgt, srcn = n_id[ei[1]], n_id[ei[0]]
+        # srcn must sit in tgt's row: indices[p] == srcn for some p in [indptr[tgt], indptr[tgt+1]) -- invert the formula
+        # row by row on a sample of edges
+        pick = torch.randperm(ei.shape[1], device="cuda")[:2000]
+        for t, s in zip(tgt[pick].tolist(), srcn[pick].tolist()):
+            lo, hi = int(indptr[t]), int(indptr[t + 1])
+            assert bool((indices[lo:hi] == s).any())
+
+
+def test_rmat_graph_khop_and_gather_bit_exact(oracle):
+    """BASELINE config 2 shape at 1/16 scale (R-MAT (0.57,0.19,0.19,0.05), 0.6 M nodes, ~8 M edges with duplicate
+    neighbours and ~half the rows empty, fan-out [15,10,5], 256-d fp32): k-hop ids and edge_index bit-exact with the
+    oracle, gathered rows equal x[n_id]."""
+    import quiver
+    from graphs import rmat_csr
+    n = 600_000
+    indptr, indices = rmat_csr(20, 10_000_000, n_nodes=n, seed=2)
+    assert (np.diff(indptr) == 0).mean() > 0.2 and np.diff(indptr).max() > 5_000
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [15, 10, 5], device=0, mode="GPU")
+    x = torch.from_numpy(np.random.default_rng(0).integers(0, 10, (n, 256)).astype(np.float32))
+    feature = quiver.Feature(rank=0, device_list=[0], device_cache_size="300M", cache_policy="device_replicate",
+                             csr_topo=topo)  # ~half of the rows in HBM (degree-ordered), the rest in pinned host memory
+    feature.from_cpu_tensor(x)
+    rng = np.random.default_rng(5)
+    for it in range(2):
+        seeds = rng.permutation(n)[:1024]
+        n_id, bs, adjs, rows = sampler.sample_and_gather(torch.from_numpy(seeds), feature)
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [15, 10, 5])
+        assert bs == 1024 and torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+        for adj, (o_ei, o_size) in zip(adjs, o_adjs):
+            assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)
+        assert torch.equal(rows.cpu(), x[n_id.cpu()])

@@ -134,10 +134,11 @@ class Feature(object):
         assert len(device_config.gpu_parts) == len(self.device_list)
 
         def materialise(part):
-            part = _load_part(part)
+            if isinstance(part, str):  # a saved tensor of rows (partition.py:234-247 layout): the data itself
+                return _load_part(part)
             if np_array is None:
                 return part.to(dtype=torch.float32)
-            return torch.from_numpy(np_array[part.numpy()]).to(dtype=torch.float32)
+            return torch.from_numpy(np_array[part.numpy()]).to(dtype=torch.float32)  # the part lists row ids of the mmap
 
         if self.cache_policy == "device_replicate":
             for device in self.device_list:
