@@ -958,6 +958,39 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Every hop's emit in one launch at the end of the k-hop.  A node keeps the local id it got when it was first seen
+// (later hops only atomicMin candidates > 2^31 over it), so the col_idx of hop h can be read from the map any time after
+// hop h's scan: nothing on the hop-to-hop critical path waits for it.  Thread t serves edge t - begin[h] of hop h, with
+// begin[] the prefix of the hops' static edge bounds.
+struct EmitAll {
+    const int64_t *nbr[QV_MAX_HOPS];
+    const int64_t *d_E[QV_MAX_HOPS];
+    int64_t *col[QV_MAX_HOPS];
+    int64_t begin[QV_MAX_HOPS + 1];
+    int n_hops;
+};
+
+__global__ void __launch_bounds__(256)
+    map_emit_all_kernel(const __grid_constant__ EmitAll p, const MapWord *__restrict__ map, int64_t n_nodes)
+{
+    pdl_wait();
+    pdl_release();
+    const int64_t total = p.begin[p.n_hops];
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int h = 0;
+#pragma unroll
+        for (int i = 1; i < QV_MAX_HOPS; i++)
+            if (i < p.n_hops && t >= p.begin[i]) h = i;
+        const int64_t e = t - p.begin[h];
+        if (e >= *p.d_E[h]) continue;
+        const int64_t key = p.nbr[h][e];
+        p.col[h][e] = static_cast<uint64_t>(key) < static_cast<uint64_t>(n_nodes)
+                          ? static_cast<int64_t>(static_cast<unsigned int>(map[key]) & 0x7FFFFFFFu)
+                          : 0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     max_degree_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, unsigned long long *__restrict__ result)
 {
@@ -1471,8 +1504,12 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
              bool *id_error, const GatherTail &tail)
 {
     int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
-    int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
+    int64_t *nbr_base = static_cast<int64_t *>(s->nbr.ptr);
     MapWord *map = static_cast<MapWord *>(s->node_map.ptr);
+    static const bool emit_per_hop = getenv("QV_EMIT_PER_HOP") && getenv("QV_EMIT_PER_HOP")[0] == '1';  // A-B switch
+    EmitAll emit;
+    memset(&emit, 0, sizeof emit);
+    emit.n_hops = n_hops;
     int64_t *d_err = s->d_meta + kMetaErr;
     *id_error = false;
     unsigned int epoch_hi = 0;
@@ -1503,6 +1540,12 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         int64_t *d_F = m + kMetaF;
         const int64_t *hop_seeds = h == 0 ? seeds : n_id;
         int64_t *d_next_S = m + kMetaStride + kMetaS;  // the next hop's seed count is this hop's frontier size
+        // the sampled ids of every hop stay alive until the single emit at the end (map path); the hash path reuses one region
+        int64_t *nbr = nbr_base + (use_map ? emit.begin[h] : 0);
+        emit.nbr[h] = nbr;
+        emit.d_E[h] = d_E;
+        emit.col[h] = edge_buf[h];
+        emit.begin[h + 1] = emit.begin[h] + be[h];
         HopExtras x;
         int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start ? fr_start + bn[n_hops] : nullptr;
         if (use_map) {
@@ -1552,12 +1595,17 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             else QV_MAP_SCAN(4, false);
 #undef QV_MAP_SCAN
             QV_CHECK_LAUNCH("map_scan_kernel");
-            if (be[h] > 0) {
+            if (emit_per_hop && be[h] > 0) {
                 QV_CUDA(launch_chained(map_emit_kernel, grid_for(be[h], 256, s->n_sm), 256, 0, st, nbr, d_E, map,
                                        s->n_nodes, edge_buf[h]));
                 QV_CHECK_LAUNCH("map_emit_kernel");
             }
         }
+    }
+    if (use_map && !emit_per_hop && emit.begin[n_hops] > 0) {
+        QV_CUDA(launch_chained(map_emit_all_kernel, grid_for(emit.begin[n_hops], 256, s->n_sm), 256, 0, st, emit, map,
+                               s->n_nodes));
+        QV_CHECK_LAUNCH("map_emit_all_kernel");
     }
     QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     QV_CUDA(cudaEventRecord(s->meta_ready, st));
@@ -1630,7 +1678,9 @@ int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *si
                    s->n_nodes <= (int64_t(1) << 30) && bn[n_hops] < (int64_t(1) << 31);
     QV_TRY(ensure_scan(s, bn[n_hops]));
     QV_TRY(s->out_ptr.ensure(static_cast<size_t>(max_nodes) * sizeof(int64_t)));
-    QV_TRY(s->nbr.ensure(static_cast<size_t>(std::max<int64_t>(max_edges, 1)) * sizeof(int64_t)));
+    int64_t sum_edges = 0;
+    for (int h = 0; h < n_hops; h++) sum_edges += be[h];
+    QV_TRY(s->nbr.ensure(static_cast<size_t>(std::max<int64_t>(sum_edges, 1)) * sizeof(int64_t)));
     if (use_map && !s->node_map.ptr) {
         if (s->node_map.ensure(static_cast<size_t>(s->n_nodes) * sizeof(MapWord)) != QV_OK) use_map = false;  // no room
         s->map_epoch = 0;
