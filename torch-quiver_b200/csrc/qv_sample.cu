@@ -91,6 +91,7 @@ constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
 struct ScanState {
     unsigned long long *words;  // [0] = ticket, [1 + tile] = descriptor; zeroed before each launch
+    int direct = 0;             // 1: tile = blockIdx.x (the host checked that the whole grid fits on the device at once)
 };
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
@@ -181,8 +182,12 @@ __device__ __forceinline__ long long chained_scan(long long thread_sum, ScanStat
     return tile_excl_sh + warp_base + (incl - thread_sum);
 }
 
+// A tile may only wait on tiles that are certain to run.  Tickets guarantee that for any grid size at the cost of one
+// atomic round trip before the tile's first load; when every block of the grid can be resident at the same time each
+// block is bound to be scheduled whatever the others spin on, so the block index serves as the tile index directly.
 __device__ __forceinline__ int take_ticket(ScanState st)
 {
+    if (st.direct) return static_cast<int>(blockIdx.x);
     __shared__ int tile_sh;
     if (threadIdx.x == 0) tile_sh = static_cast<int>(atomicAdd(st.words, 1ull));
     __syncthreads();
@@ -1009,12 +1014,6 @@ __global__ void __launch_bounds__(256) recip_table_kernel(unsigned long long *__
         recip[m] = m < 2 ? 0ull : (0xFFFFFFFFFFFFFFFFull / m + 1ull);
 }
 
-__global__ void init_khop_meta_kernel(int64_t *meta, int64_t S, int err_idx)
-{
-    meta[kMetaS] = S;
-    meta[err_idx] = 0;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // cal_next (cuda_random.cu.hpp:71-104): one hop of access-probability propagation,
 //   p'[v] = 1 - (1 - p[v]) * prod_{u in N(v)} skip(u),   skip(u) = 1 - p[u] * min(1, k / deg u)   (1 when deg u = 0).
@@ -1089,6 +1088,23 @@ struct Buffer {
     }
 };
 
+// Blocks of `kernel` (kScanThreads threads, no dynamic shared memory) that can be resident on the device at once.
+template <typename K>
+int resident_capacity(K kernel, int n_sm)
+{
+    static int per_sm = -1;  // one instance per kernel type
+    if (per_sm < 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kScanThreads, 0) != cudaSuccess) {
+            cudaGetLastError();
+            v = 0;
+        }
+        per_sm = v;
+    }
+    static const bool off = getenv("QV_SCAN_TICKETS") && getenv("QV_SCAN_TICKETS")[0] == '1';  // A-B switch
+    return off ? 0 : per_sm * n_sm;
+}
+
 inline int tiles_for(int64_t n) { return static_cast<int>(std::max<int64_t>(1, (n + kScanTile - 1) / kScanTile)); }
 inline int host_log2_cap(int64_t n_items)
 {
@@ -1125,6 +1141,7 @@ struct qv_sampler {
     Buffer fr_meta;   // [2][bound] int64: CSR row start / degree of every frontier node (fused k-hop path)
     Buffer node_map;  // MapWord per graph node: epoch-tagged first-occurrence map of the fused k-hop path
     unsigned int map_epoch = 0;  // 0 = the map has never been initialised
+    bool err_dirty = false;      // the device error flag (kMetaErr) is set and must be cleared before the next k-hop
     bool fast = false;           // opt-in non-reference sampling (qv_sampler_set_fast)
     uint64_t fast_calls = 0;     // call counter mixed into the fast sampler's key
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
@@ -1224,8 +1241,10 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
                       const HopExtras &x = HopExtras())
 {
     const int n_tiles = tiles_for(S_bound);
+    ScanState scan = scan_region(s, region);
+    scan.direct = n_tiles <= resident_capacity(count_scan_kernel, s->n_sm);
     QV_CUDA(launch_chained(count_scan_kernel, n_tiles, kScanThreads, 0, st, s->indptr, s->n_nodes, seeds, S_arg, d_S, k,
-                           counts, out_ptr, d_total, scan_region(s, region), n_tiles, x.cached_deg,
+                           counts, out_ptr, d_total, scan, n_tiles, x.cached_deg,
                            x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err));
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
@@ -1521,8 +1540,10 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         s->map_epoch++;  // every call (also a failed one) gets its own epoch: older words never need clearing
         epoch_hi = 0xFFFFFFFFu - s->map_epoch;
     }
-    init_khop_meta_kernel<<<1, 1, 0, st>>>(s->d_meta, S, kMetaErr);
-    QV_CHECK_LAUNCH("init_khop_meta_kernel");
+    if (s->err_dirty) {  // the flag is only ever raised by a call that saw a bad id: clear it after such a call, not always
+        QV_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int64_t), st));
+        s->err_dirty = false;
+    }
     // one memset clears the scan descriptors of every hop (each hop owns regions 2h and 2h+1)
     if (s->scan_region_words * 2 * n_hops <= (size_t(1) << 20)) {
         QV_CUDA(cudaMemsetAsync(s->scan.ptr, 0, s->scan_region_words * 2 * n_hops * sizeof(unsigned long long), st));
@@ -1535,7 +1556,9 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
     }
     for (int h = 0; h < n_hops; h++) {
         int64_t *m = s->d_meta + kMetaStride * h;
-        const int64_t *d_S = m + kMetaS;
+        // hop 0's seed count is known on the host; later hops read the previous hop's frontier size on the device
+        const int64_t S_h = h == 0 ? S : 0;
+        const int64_t *d_S = h == 0 ? nullptr : m + kMetaS;
         int64_t *d_E = m + kMetaE;
         int64_t *d_F = m + kMetaF;
         const int64_t *hop_seeds = h == 0 ? seeds : n_id;
@@ -1552,14 +1575,14 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             x.node_map = map;
             x.epoch_hi = epoch_hi;
             x.d_err = d_err;
-            x.d_item_base = h == 0 ? d_S : nullptr;  // items of hop 0 are [seeds | outputs]; later hops: outputs only
+            x.item_base = h == 0 ? S : 0;  // items of hop 0 are [seeds | outputs]; later hops: outputs only
             if (h >= 1 && fr_start) {
                 x.cached_start = fr_start;
                 x.cached_deg = fr_deg;
             }
         }
         bool fused_insert = false;
-        QV_TRY(launch_count_scan(s, hop_seeds, 0, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
+        QV_TRY(launch_count_scan(s, hop_seeds, S_h, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
         // Inserting the sampled ids into the node map from inside the sampling kernel: for a large hop it was measured
         // slower (+14 us on the kernel's critical blocks vs 9 us for a separate, perfectly parallel insert kernel), for a
         // small hop it was neutral (saved launch vs longer kernel): off unless QV_FUSE_INSERT_BELOW is set.
@@ -1567,17 +1590,17 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         HopExtras xs = x;
         if (bn[h] > fuse_below) xs.node_map = nullptr;
         // edge_buf[h] = [col (source local ids) | row (target = seed position)], each E long, E read on the device
-        QV_TRY(launch_sample(s, hop_seeds, 0, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st, xs,
+        QV_TRY(launch_sample(s, hop_seeds, S_h, d_S, bn[h], sizes[h], rand_seed, optr, nbr, edge_buf[h], d_E, st, xs,
                              &fused_insert, d_E, be[h]));
         if (!use_map) {
-            QV_TRY(launch_reindex(s, hop_seeds, 0, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
+            QV_TRY(launch_reindex(s, hop_seeds, S_h, d_S, bn[h], nbr, 0, d_E, be[h], n_id, d_F, edge_buf[h], nullptr,
                                   nullptr, 2 * h + 1, st, d_next_S));
         } else {
             // hop 0 also enters the seeds (they become local ids 0..S-1, duplicates merged); later hops only add
             const int64_t *prefix = h == 0 ? seeds : nullptr;
             const int64_t items = (h == 0 ? bn[0] : 0) + be[h];
             if (items > 0 && !fused_insert) {  // fan-outs > 32 use the generic sampling kernel, which does not insert
-                QV_CUDA(launch_chained(map_insert_kernel, grid_for(items, 256, s->n_sm), 256, 0, st, prefix, 0, d_S, nbr,
+                QV_CUDA(launch_chained(map_insert_kernel, grid_for(items, 256, s->n_sm), 256, 0, st, prefix, S_h, d_S, nbr,
                                        d_E, map, epoch_hi, s->n_nodes, d_err));
                 QV_CHECK_LAUNCH("map_insert_kernel");
             }
@@ -1585,10 +1608,14 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
             const bool big = items > (int64_t(4) << 20);  // below that, more (smaller) tiles hide the random-load latency better
             const int per_tile = kScanThreads * (big ? 16 : 4);
             const int n_tiles = static_cast<int>(std::max<int64_t>(1, (items + per_tile - 1) / per_tile));
+            ScanState scan = scan_region(s, 2 * h + 1);
 #define QV_MAP_SCAN(ITEMS, ROWS)                                                                                         \
-    QV_CUDA(launch_chained(map_scan_kernel<ITEMS, ROWS>, n_tiles, kScanThreads, 0, st, prefix, 0, d_S, nbr, d_E, map,  \
-                           epoch_hi, s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan_region(s, 2 * h + 1), n_tiles, s->indptr,    \
-                           fs, fd, d_next_S))
+    do {                                                                                                                 \
+        scan.direct = n_tiles <= resident_capacity(map_scan_kernel<ITEMS, ROWS>, s->n_sm);                              \
+        QV_CUDA(launch_chained(map_scan_kernel<ITEMS, ROWS>, n_tiles, kScanThreads, 0, st, prefix, S_h, d_S, nbr, d_E,   \
+                               map, epoch_hi, s->n_nodes, h == 0 ? nullptr : d_S, n_id, d_F, scan, n_tiles, s->indptr, \
+                               fs, fd, d_next_S));                                                                      \
+    } while (0)
             if (big && fd) QV_MAP_SCAN(16, true);
             else if (big) QV_MAP_SCAN(16, false);
             else if (fd) QV_MAP_SCAN(4, true);
@@ -1619,7 +1646,10 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                               tail.variant, st));
     }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
-    if (use_map && s->h_meta[kMetaErr] != 0) *id_error = true;  // the caller redoes the call on the hash path
+    if (use_map && s->h_meta[kMetaErr] != 0) {
+        *id_error = true;  // the caller redoes the call on the hash path
+        s->err_dirty = true;
+    }
     return QV_OK;
 }
 
