@@ -308,6 +308,7 @@ constexpr int kSmemSlots = 1024;                          // per warp; larger fa
 struct RecipTable {
     const unsigned long long *recip;  // [n]; recip[0] = recip[1] = 0
     unsigned int n;
+    unsigned int quick;  // 1: short rows take the unrolled path of sample_rows_small_kernel (0 = A-B switch)
 };
 
 __device__ __forceinline__ void reservoir_hit(unsigned long long M, uint32_t r, uint32_t m, uint32_t kk, uint32_t idx,
@@ -465,7 +466,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
             for (uint32_t j = 0; j < cnt; j++) rowof_w[incl - cnt + j] = static_cast<uint8_t>(lane);
         }
     }
-    for (uint32_t e = lane; e < per_warp; e += 32) slots_w[e] = e % kcap;  // every reservoir starts as 0..k-1
+    {  // every reservoir starts as 0..k-1 (e % kcap by multiply-high: exact for e < 2^16, one division per thread)
+        const uint32_t inv_k = kcap > 1 ? 0xFFFFFFFFu / kcap + 1u : 0u;
+        for (uint32_t e = lane; e < per_warp; e += 32) slots_w[e] = kcap > 1 ? e - __umulhi(e, inv_k) * kcap : 0u;
+    }
     __syncwarp();
 
     // verbatim rows: their ids can start travelling now
@@ -477,13 +481,28 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     // this lane's generator stream, row after row, no synchronisation
     {
         const uint32_t first = kk + lane;
+        const bool quick_rows = rt.quick != 0;
         const unsigned long long *tab = rt.recip + 1;  // tab[idx] = recip[idx + 1]
         const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
         for (int i = 0; i < kRowsPerWarp; i++) {
             const uint32_t d = deg_sh[w][i];
+            uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
+            if (kShortTable && d > kk && d <= tab_n && (d - kk + 31) >> 5 < kHub) {
+                // The common row (a few draws per lane): the test above is warp-uniform and the <= kHub-1 draws are fully
+                // unrolled and predicated, so there is no divergent loop, no per-lane trip count and no bound check on the
+                // table (idx < d <= tab_n); the reciprocal loads do not depend on the generator chain and issue early.
+                // (ncu source view of the previous loop: 58 warp instructions per draw round, 14 of them loop control.)
+                if (quick_rows) {
+#pragma unroll
+                    for (int t = 0; t < kHub - 1; t++) {
+                        const uint32_t idx = first + 32u * t;
+                        if (idx < d) reservoir_hit(tab[idx], xorwow_next(rng), idx + 1, kk, idx, srow);
+                    }
+                    continue;
+                }
+            }
             if (d <= first) continue;
             uint32_t rem = (d - first + 31) >> 5, idx = first;
-            uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
             if (rem >= kHub && idx + 64 * kHub < tab_n) {
                 unsigned long long M[kHub];
 #pragma unroll
@@ -1271,7 +1290,8 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     QV_TRY(rng_states_for(s, rand_seed, S_arg, d_S, S_bound, st, &states));
     const int64_t blocks = (S_bound + kSampleTile - 1) / kSampleTile;
     QV_REQUIRE(blocks < (int64_t(1) << 31), "sample: too many seeds (%lld)", (long long)S_bound);
-    const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n};
+    static const bool quick_off = getenv("QV_SAMPLE_QUICK") && getenv("QV_SAMPLE_QUICK")[0] == '0';
+    const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n, quick_off ? 0u : 1u};
     static const int impl = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;  // tuning switch
     const size_t small_smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max<int64_t>(k, 1) * 13;
     if (k >= 0 && k <= 32 && !(impl & 1)) {
