@@ -496,3 +496,30 @@ def test_rmat_graph_khop_and_gather_bit_exact(oracle):
         for adj, (o_ei, o_size) in zip(adjs, o_adjs):
             assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)
         assert torch.equal(rows.cpu(), x[n_id.cpu()])
+
+
+@pytest.mark.parametrize("n_heavy", [3, 40, 300])
+def test_longest_first_schedule_keeps_results(oracle, n_heavy):
+    """The fused k-hop runs warps that own a heavy row (> 48 draws per lane) in extra blocks at the front of the grid
+    (count_scan lists them, the regular slot retires).  Results must not move: few heavy rows, several in one warp
+    (rows r and r+4 share a warp), and more than the 64-entry list can hold (the overflow stays on the regular
+    schedule) -- ids and edge_index bit-exact with the oracle."""
+    import quiver
+    rng = np.random.default_rng(n_heavy)
+    n = 30000
+    deg = rng.integers(0, 12, n)
+    deg[:n_heavy] = rng.integers(1700, 4000, n_heavy)   # heavy: (deg - k) / 32 > 48
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, n, int(indptr[-1])).astype(np.int64)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [5, 3], device=0, mode="GPU")
+    # heavy nodes packed at the front of the seed list: rows 0, 4, 8, ... share warp 0 of tile 0
+    seeds = np.concatenate([np.arange(n_heavy), n_heavy + rng.permutation(n - n_heavy)[:700]]).astype(np.int64)
+    for _ in range(2):
+        n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [5, 3])
+        assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+        for adj, (o_ei, o_size) in zip(adjs, o_adjs):
+            assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)
+        seeds = seeds[::-1].copy()  # heavy rows at the END of the list the second time (last tiles of the grid)

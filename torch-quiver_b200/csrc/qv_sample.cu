@@ -89,6 +89,18 @@ constexpr unsigned long long kFlagAgg = 1ull << 62;
 constexpr unsigned long long kFlagPrefix = 2ull << 62;
 constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 
+// Longest-first scheduling of the sampling kernel.  A row of degree d costs its warp ~(d-k)/32 dependent generator
+// draws (parity with the reference's per-lane streams forbids splitting the chain), so the kernel's duration is
+// max over warps of (start time + chain): ncu showed one SM still busy for 37 k cycles after all others had finished
+// a 106 k-cycle launch.  count_scan therefore lists the warps that own a row with more than kHeavyDraws draws per lane
+// (entry = tile * 4 + warp), and the sampling kernel runs those entries in extra blocks at the FRONT of the grid while
+// the warp's regular slot finds itself in the list and retires: the long chains start at time zero instead of wherever
+// their tile happens to be scheduled.  Same work, same results; list overflow or no list = regular schedule.
+constexpr int kHeavyCap = 64;                    // listed warps per launch
+constexpr int kHeavyDraws = 48;                  // draws per lane that make a row "heavy" (deg - k > 32 * kHeavyDraws)
+constexpr int kHeavyWords = 1 + kHeavyCap;       // [0] = count, [1..] = entries; lives at the end of a scan region
+constexpr int kHeavyBlocks = kHeavyCap / 4;      // worker blocks: one listed warp per physical warp
+
 struct ScanState {
     unsigned long long *words;  // [0] = ticket, [1 + tile] = descriptor; zeroed before each launch
     int direct = 0;             // 1: tile = blockIdx.x (the host checked that the whole grid fits on the device at once)
@@ -210,6 +222,13 @@ __device__ __forceinline__ MapWord map_word(unsigned int epoch_hi, unsigned int 
     return (static_cast<MapWord>(epoch_hi) << 32) | payload;
 }
 
+// Row r belongs to warp (r & 3) of tile (r >> 6) in the reference geometry (cuda_random.cu.hpp:17-20).
+__device__ __forceinline__ void note_heavy_row(unsigned long long *heavy, int64_t r)
+{
+    const unsigned long long at = atomicAdd(heavy, 1ull);
+    if (at < kHeavyCap) heavy[1 + at] = (static_cast<unsigned long long>(r >> 6) << 2) | static_cast<unsigned long long>(r & 3);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Kernel A: counts[i] = min(deg(seed_i), k), out_ptr = exclusive scan, total.   (quiver_sample.cu:157-169)
 // ------------------------------------------------------------------------------------------------------------------
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(kScanThreads)
                       int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k, int64_t *__restrict__ counts,
                       int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles,
                       const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
-                      int64_t *__restrict__ d_err)
+                      int64_t *__restrict__ d_err, unsigned long long *__restrict__ heavy)
 {
     pdl_wait();
     pdl_release();
@@ -235,11 +254,13 @@ __global__ void __launch_bounds__(kScanThreads)
             if (cached_deg) {  // hop >= 1 of a fused k-hop: the frontier's degrees were recorded when its nodes joined
                 const int64_t deg = cached_deg[i];
                 v = (k >= 0 && deg > k) ? k : deg;
+                if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i);
             } else {
                 const int64_t node = seeds[i];
                 if (node >= 0 && node < n_nodes) {
                     const int64_t deg = indptr[node + 1] - indptr[node];
                     v = (k >= 0 && deg > k) ? k : deg;
+                    if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i);
                     if (node_map)  // hop 0: seeds enter the node map
                         atomicMin(&node_map[node], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(i)));
                 } else if (node_map) {
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                              const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
                              const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
                              int64_t item_base_arg, const int64_t *__restrict__ d_item_base,
-                             int64_t *__restrict__ d_err)
+                             int64_t *__restrict__ d_err, const unsigned long long *__restrict__ heavy)
 {
     // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
     // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
@@ -413,18 +434,34 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
     pdl_wait();
     const int64_t S = dev_size(S_arg, d_S);
-    const int64_t b = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int wp = threadIdx.x >> 5;  // physical warp: owns a slice of the shared-memory arrays
+    int w = wp;                       // logical warp of the reference geometry: decides rows and generator streams
+    int64_t b = blockIdx.x;
+    bool listed_run = false;
+    if (heavy) {  // longest-first schedule: the first kHeavyBlocks blocks run the listed (heavy) warps
+        if (blockIdx.x < kHeavyBlocks) {
+            const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
+            const unsigned int slot = blockIdx.x * kSampleWarps + wp;
+            if (slot >= n_listed) return;
+            const unsigned long long entry = heavy[1 + slot];
+            b = static_cast<int64_t>(entry >> 2);
+            w = static_cast<int>(entry & 3);
+            listed_run = true;
+        } else {
+            b = blockIdx.x - kHeavyBlocks;
+        }
+    }
     if (b * kSampleTile >= S) return;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t kk = static_cast<uint32_t>(k);
-    int64_t *stage_w = reinterpret_cast<int64_t *>(dyn_smem) + static_cast<size_t>(w) * per_warp;
+    int64_t *stage_w = reinterpret_cast<int64_t *>(dyn_smem) + static_cast<size_t>(wp) * per_warp;
     uint32_t *slots_w = reinterpret_cast<uint32_t *>(dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 8) +
-                        static_cast<size_t>(w) * per_warp;
-    uint8_t *rowof_w = dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 12 + static_cast<size_t>(w) * per_warp;
+                        static_cast<size_t>(wp) * per_warp;
+    uint8_t *rowof_w = dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 12 + static_cast<size_t>(wp) * per_warp;
 
     Xorwow rng;
     {
-        const uint32_t *p = rng_states + static_cast<size_t>(b) * kRngStateWords * kRngBlockThreads + threadIdx.x;
+        const uint32_t *p = rng_states + static_cast<size_t>(b) * kRngStateWords * kRngBlockThreads + (w * 32 + lane);
         rng.d = p[0 * kRngBlockThreads];
         rng.v0 = p[1 * kRngBlockThreads];
         rng.v1 = p[2 * kRngBlockThreads];
@@ -450,6 +487,14 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                 }
             }
         }
+        if (heavy && !listed_run && __any_sync(0xffffffffu, my_deg - k > 32 * kHeavyDraws)) {
+            // this warp owns a heavy row: if count_scan managed to list it, a front-of-grid block is already on it
+            const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
+            const unsigned long long me = (static_cast<unsigned long long>(b) << 2) | static_cast<unsigned long long>(w);
+            bool found = false;
+            for (unsigned int j = lane; j < n_listed; j += 32) found |= heavy[1 + j] == me;
+            if (__any_sync(0xffffffffu, found)) return;
+        }
         const uint32_t cnt = static_cast<uint32_t>(my_deg <= k ? my_deg : k);
         uint32_t incl = cnt;
 #pragma unroll
@@ -459,10 +504,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         }
         n_entries = __shfl_sync(0xffffffffu, incl, kRowsPerWarp - 1);
         if (lane < kRowsPerWarp) {
-            deg_sh[w][lane] = static_cast<uint32_t>(min(my_deg, static_cast<int64_t>(0xffffffffu)));
-            start_sh[w][lane] = my_start;
-            o_sh[w][lane] = my_o;
-            pre_sh[w][lane] = static_cast<uint16_t>(incl - cnt);
+            deg_sh[wp][lane] = static_cast<uint32_t>(min(my_deg, static_cast<int64_t>(0xffffffffu)));
+            start_sh[wp][lane] = my_start;
+            o_sh[wp][lane] = my_o;
+            pre_sh[wp][lane] = static_cast<uint16_t>(incl - cnt);
             for (uint32_t j = 0; j < cnt; j++) rowof_w[incl - cnt + j] = static_cast<uint8_t>(lane);
         }
     }
@@ -475,7 +520,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     // verbatim rows: their ids can start travelling now
     for (uint32_t e = lane; e < n_entries; e += 32) {
         const int i = rowof_w[e];
-        if (deg_sh[w][i] <= kk) cp_async_8(&stage_w[e], indices + start_sh[w][i] + (e - pre_sh[w][i]));
+        if (deg_sh[wp][i] <= kk) cp_async_8(&stage_w[e], indices + start_sh[wp][i] + (e - pre_sh[wp][i]));
     }
 
     // this lane's generator stream, row after row, no synchronisation
@@ -485,7 +530,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         const unsigned long long *tab = rt.recip + 1;  // tab[idx] = recip[idx + 1]
         const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
         for (int i = 0; i < kRowsPerWarp; i++) {
-            const uint32_t d = deg_sh[w][i];
+            const uint32_t d = deg_sh[wp][i];
             uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
             if (kShortTable && d > kk && d <= tab_n && (d - kk + 31) >> 5 < kHub) {
                 // The common row (a few draws per lane): the test above is warp-uniform and the <= kHub-1 draws are fully
@@ -566,15 +611,15 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     // sampled rows: fetch the chosen positions; then one wait and one coalesced write-out of the whole list
     for (uint32_t e = lane; e < n_entries; e += 32) {
         const int i = rowof_w[e];
-        if (deg_sh[w][i] > kk)
-            cp_async_8(&stage_w[e], indices + start_sh[w][i] + slots_w[static_cast<size_t>(i) * kcap + (e - pre_sh[w][i])]);
+        if (deg_sh[wp][i] > kk)
+            cp_async_8(&stage_w[e], indices + start_sh[wp][i] + slots_w[static_cast<size_t>(i) * kcap + (e - pre_sh[wp][i])]);
     }
     cp_async_wait_all();
     const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
     const int64_t item_base = node_map ? (d_item_base ? *d_item_base : item_base_arg) : 0;
     for (uint32_t e = lane; e < n_entries; e += 32) {
         const int i = rowof_w[e];
-        const int64_t dst = o_sh[w][i] + (e - pre_sh[w][i]);
+        const int64_t dst = o_sh[wp][i] + (e - pre_sh[wp][i]);
         const int64_t id = stage_w[e];
         out[dst] = id;
         if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
@@ -1174,7 +1219,7 @@ constexpr int kScanRegions = 2 * QV_MAX_HOPS;  // two scans per hop, every hop o
 
 int ensure_scan(qv_sampler *s, int64_t max_items)
 {
-    const size_t words = static_cast<size_t>(tiles_for(max_items)) + 2;
+    const size_t words = static_cast<size_t>(tiles_for(max_items)) + 2 + kHeavyWords;  // descriptors + longest-first list
     const size_t region = (words + 15) & ~size_t(15);
     if (region > s->scan_region_words) {
         QV_TRY(s->scan.ensure(region * kScanRegions * sizeof(unsigned long long)));
@@ -1185,6 +1230,10 @@ int ensure_scan(qv_sampler *s, int64_t max_items)
 ScanState scan_region(qv_sampler *s, int which)
 {
     return ScanState{static_cast<unsigned long long *>(s->scan.ptr) + which * s->scan_region_words};
+}
+unsigned long long *heavy_region(qv_sampler *s, int which)  // the last kHeavyWords of a scan region
+{
+    return scan_region(s, which).words + s->scan_region_words - kHeavyWords;
 }
 int zero_scan_regions(qv_sampler *s, int64_t items0, int64_t items1, cudaStream_t st)
 {
@@ -1253,6 +1302,7 @@ struct HopExtras {  // fused k-hop only; all null for the standalone calls
     int64_t item_base = 0;
     const int64_t *d_item_base = nullptr;
     int64_t *d_err = nullptr;
+    unsigned long long *heavy = nullptr;  // longest-first list (kHeavyWords, zeroed): filled by count_scan, read by the sampler
 };
 
 int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
@@ -1264,7 +1314,7 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
     scan.direct = n_tiles <= resident_capacity(count_scan_kernel, s->n_sm);
     QV_CUDA(launch_chained(count_scan_kernel, n_tiles, kScanThreads, 0, st, s->indptr, s->n_nodes, seeds, S_arg, d_S, k,
                            counts, out_ptr, d_total, scan, n_tiles, x.cached_deg,
-                           x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err));
+                           x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err, x.heavy));
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
 }
@@ -1296,14 +1346,17 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     const size_t small_smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max<int64_t>(k, 1) * 13;
     if (k >= 0 && k <= 32 && !(impl & 1)) {
         if (!(impl & 4))  // default: fastmod table for short rows too (measured -10 us per bench step vs plain %)
-            QV_CUDA(launch_chained(sample_rows_small_kernel<true, 4, 8>, static_cast<unsigned>(blocks), kSampleWarps * 32,
+            QV_CUDA(launch_chained(sample_rows_small_kernel<true, 4, 8>,
+                                   static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)), kSampleWarps * 32,
                                    small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
                                    static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
-                                   x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err));
+                                   x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err, x.heavy));
         else
-            sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks), kSampleWarps * 32, small_smem, st>>>(
+            sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)),
+                                                    kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
-                row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err);
+                row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err,
+                x.heavy);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
@@ -1570,6 +1623,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
     } else {
         for (int h = 0; h < n_hops; h++) {
             QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h).words, 0, (tiles_for(bn[h]) + 2) * sizeof(unsigned long long), st));
+            QV_CUDA(cudaMemsetAsync(heavy_region(s, 2 * h), 0, sizeof(unsigned long long), st));
             QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h + 1).words, 0,
                                     (tiles_for(bn[h] + be[h]) + 2) * sizeof(unsigned long long), st));
         }
@@ -1601,6 +1655,12 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
                 x.cached_deg = fr_deg;
             }
         }
+        // longest-first schedule of the sampling kernel (small-fan-out kernel only; QV_HEAVY_FIRST=0 is the A-B switch)
+        static const bool heavy_off = getenv("QV_HEAVY_FIRST") && getenv("QV_HEAVY_FIRST")[0] == '0';
+        static const int impl_sw = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;
+        if (!heavy_off && !s->fast && sizes[h] >= 0 && sizes[h] <= 32 && !(impl_sw & 1) &&
+            s->max_degree - sizes[h] > 32 * kHeavyDraws)
+            x.heavy = heavy_region(s, 2 * h);
         bool fused_insert = false;
         QV_TRY(launch_count_scan(s, hop_seeds, S_h, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
         // Inserting the sampled ids into the node map from inside the sampling kernel: for a large hop it was measured
