@@ -107,17 +107,30 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own CPU implementation of the path (oracle/_ref when built)
 # ----------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    """All the host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, which would leave the reference's
+    CPU gather (and its OpenMP build) on one core: undo that for the reference arm."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def reference_cpu_setup(indptr_cpu, indices_cpu):
+    """The reference CPU extension compiled from its own sources (oracle/_ref).  Default: the as-shipped build (its
+    at::parallel_for runs serially without -fopenmp, setup.py:58-69); QV_REF_VARIANT=omp selects the -fopenmp build (both
+    register the same pybind types, so one process can only hold one; measured here: 0.40 s vs 0.46 s per batch for the
+    sampler -- reindex_single is serial in both).  The CPU gather uses every host thread either way."""
     from oracle import oracle
-    best = None
-    for openmp in (False, True):
+    host_threads()
+    order = (True, False) if os.environ.get("QV_REF_VARIANT", "") == "omp" else (False, True)
+    for openmp in order:
         ext = oracle.load_reference(openmp=openmp)
         if ext is not None:
-            best = best or (ext, openmp)
-    if best is None:
-        return None
-    ext, openmp = best
-    return {"ext": ext, "openmp": openmp, "quiver": ext.cpu_quiver_from_csr_array(indptr_cpu, indices_cpu)}
+            return {"ext": ext, "openmp": openmp, "quiver": ext.cpu_quiver_from_csr_array(indptr_cpu, indices_cpu)}
+    return None
 
 
 def reference_cpu_step(ref, seeds, x_cpu):
@@ -144,11 +157,11 @@ def run_reference(args, rank, world):
     indptr, indices = make_graph(dev)
     indptr_cpu, indices_cpu = indptr.cpu(), indices.cpu()
     del indptr, indices
+    x_cpu = torch.rand(N_NODES, FEAT_DIM)
+    batches = make_seed_batches(args.steps + args.warmup)
     ref = reference_cpu_setup(indptr_cpu, indices_cpu)
     if ref is None:
         return {"impl": "reference", "unavailable": "oracle/_ref (reference CPU extension) was not built"}
-    x_cpu = torch.rand(N_NODES, FEAT_DIM)
-    batches = make_seed_batches(args.steps + args.warmup)
     for b in batches[:args.warmup]:
         reference_cpu_step(ref, b, x_cpu)
     edges = rows = 0
@@ -484,7 +497,7 @@ def run_ours(args, rank, world, local_rank):
                 "sample": f"{n_b} batches of the same workload; reference CPU extension compiled from its sources "
                           f"(as shipped: serial at::parallel_for) for sample+reindex, torch CPU gather on "
                           f"{torch.get_num_threads()} threads; host has {os.cpu_count()} cores",
-                "seps_sampler_only": e / ts, "feature_gather_GiBps": r * row_bytes / tg / 2**30}
+                    "seps_sampler_only": e / ts, "feature_gather_GiBps": r * row_bytes / tg / 2**30}
         else:
             out["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference",
                                    "sample": "oracle/_ref not built"}
