@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                              const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
                              const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
                              int64_t item_base_arg, const int64_t *__restrict__ d_item_base,
-                             int64_t *__restrict__ d_err, const unsigned long long *__restrict__ heavy)
+                             int64_t *__restrict__ d_err, const unsigned long long *__restrict__ heavy, int late_wait)
 {
     // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
     // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
@@ -432,7 +432,12 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     __shared__ int64_t o_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint32_t deg_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
-    pdl_wait();
+    // Programmatic dependent launch, taken one step further: the kernel in front of this one is count_scan, whose blocks
+    // release their dependents only after they have themselves waited for the hop's inputs (frontier rows, sizes), so
+    // those are complete when a block of this kernel starts.  What count_scan PRODUCES (out_ptr, the longest-first list)
+    // is needed only for the final write-out -- the wait sits there (late_wait), and count_scan runs underneath this
+    // kernel's prologue and generator loop instead of in front of it (QV_PDL_LATE=0 restores the wait at the top).
+    if (!late_wait) pdl_wait();
     const int64_t S = dev_size(S_arg, d_S);
     const int lane = threadIdx.x & 31;
     const int wp = threadIdx.x >> 5;  // physical warp: owns a slice of the shared-memory arrays
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     bool listed_run = false;
     if (heavy) {  // longest-first schedule: the first kHeavyBlocks blocks run the listed (heavy) warps
         if (blockIdx.x < kHeavyBlocks) {
+            pdl_wait();  // the list is count_scan's output
             const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
             const unsigned int slot = blockIdx.x * kSampleWarps + wp;
             if (slot >= n_listed) return;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         int64_t my_start = 0, my_deg = 0, my_o = 0;
         const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
         if (lane < kRowsPerWarp && r < S) {
-            my_o = out_ptr[r];
+            if (!late_wait) my_o = out_ptr[r];
             if (cached_deg) {
                 my_start = cached_start[r];
                 my_deg = cached_deg[r];
@@ -489,6 +495,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         }
         if (heavy && !listed_run && __any_sync(0xffffffffu, my_deg - k > 32 * kHeavyDraws)) {
             // this warp owns a heavy row: if count_scan managed to list it, a front-of-grid block is already on it
+            pdl_wait();
             const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
             const unsigned long long me = (static_cast<unsigned long long>(b) << 2) | static_cast<unsigned long long>(w);
             bool found = false;
@@ -613,6 +620,12 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         const int i = rowof_w[e];
         if (deg_sh[wp][i] > kk)
             cp_async_8(&stage_w[e], indices + start_sh[wp][i] + slots_w[static_cast<size_t>(i) * kcap + (e - pre_sh[wp][i])]);
+    }
+    if (late_wait) {  // only now are count_scan's offsets needed
+        pdl_wait();
+        const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
+        if (lane < kRowsPerWarp && r < S) o_sh[wp][lane] = out_ptr[r];
+        __syncwarp();
     }
     cp_async_wait_all();
     const int64_t row_off = row_out ? (d_row_off ? *d_row_off : 0) : 0;
@@ -1303,6 +1316,7 @@ struct HopExtras {  // fused k-hop only; all null for the standalone calls
     const int64_t *d_item_base = nullptr;
     int64_t *d_err = nullptr;
     unsigned long long *heavy = nullptr;  // longest-first list (kHeavyWords, zeroed): filled by count_scan, read by the sampler
+    int late_wait = 0;                    // the sampling kernel waits for count_scan only before its write-out
 };
 
 int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
@@ -1350,13 +1364,14 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
                                    static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)), kSampleWarps * 32,
                                    small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
                                    static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
-                                   x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err, x.heavy));
+                                   x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err, x.heavy,
+                                   x.late_wait));
         else
             sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)),
                                                     kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
                 row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err,
-                x.heavy);
+                x.heavy, 0);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
@@ -1661,6 +1676,9 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         if (!heavy_off && !s->fast && sizes[h] >= 0 && sizes[h] <= 32 && !(impl_sw & 1) &&
             s->max_degree - sizes[h] > 32 * kHeavyDraws)
             x.heavy = heavy_region(s, 2 * h);
+        // count_scan directly in front of the sampling kernel (rand_seed 0: no state-fill kernel in between): overlap them
+        static const bool late_off = getenv("QV_PDL_LATE") && getenv("QV_PDL_LATE")[0] == '0';
+        x.late_wait = (!late_off && rand_seed == 0 && !s->fast) ? 1 : 0;
         bool fused_insert = false;
         QV_TRY(launch_count_scan(s, hop_seeds, S_h, d_S, bn[h], sizes[h], nullptr, optr, d_E, 2 * h, st, x));
         // Inserting the sampled ids into the node map from inside the sampling kernel: for a large hop it was measured
