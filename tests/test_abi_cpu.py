@@ -86,3 +86,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_xorwow_jump_ahead_equals_sequential_stepping(tmp_path):
+    """The chain splitting of mega rows positions generators with xorwow_jump (GF(2) matrices A^(2^i), qv_xorwow.cuh).
+    The function is __host__ __device__: a host build of tests/native/xorwow_jump_test.cu checks it against stepping the
+    generator draw by draw (offsets 0 .. 1,000,003 on several seeds)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    csrc = os.path.join(ROOT, "torch-quiver_b200", "csrc")
+    exe = str(tmp_path / "jump_test")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-I", os.path.join(ROOT, "include"),
+                           "-I", csrc, os.path.join(ROOT, "tests", "native", "xorwow_jump_test.cu"),
+                           os.path.join(csrc, "qv_xorwow.cu"), os.path.join(csrc, "qv_runtime.cu"), "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    assert "jump ok" in out

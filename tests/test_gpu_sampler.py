@@ -523,3 +523,36 @@ def test_longest_first_schedule_keeps_results(oracle, n_heavy):
         for adj, (o_ei, o_size) in zip(adjs, o_adjs):
             assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)
         seeds = seeds[::-1].copy()  # heavy rows at the END of the list the second time (last tiles of the grid)
+
+
+@pytest.mark.parametrize("n_mega,sizes", [(1, [5, 3]), (3, [15, 10]), (11, [5, 3])])
+def test_mega_rows_chain_splitting_is_bit_exact(oracle, n_mega, sizes):
+    """Rows with more than 1024 draws per lane (degree > 32 k) are not walked by their warp: front-of-grid workers run
+    256-draw segments from generator states obtained by GF(2) jump-ahead, the owner jumps over the row.  Must equal the
+    sequential chain exactly: one mega row, several (two in one warp: seed positions 0 and 4; one as a warp's last row:
+    position 60), more than the 8 the launch can list, and mega rows again in the second hop (the frontier keeps the seeds
+    in front).  Degrees up to 150 k."""
+    import quiver
+    rng = np.random.default_rng(100 + n_mega)
+    n = 60000
+    deg = rng.integers(0, 10, n)
+    mega_deg = rng.integers(33_000, 60_000, n_mega)
+    mega_deg[0] = 150_000
+    deg[:n_mega] = mega_deg
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, n, int(indptr[-1])).astype(np.int64)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, sizes, device=0, mode="GPU")
+    others = n_mega + rng.permutation(n - n_mega)[:400]
+    seeds = others.copy()
+    slots = [0, 4, 60, 7, 129, 130, 200, 201, 202, 203, 300][:n_mega]  # seed positions of the mega nodes
+    seeds[slots] = np.arange(n_mega)
+    seeds = seeds.astype(np.int64)
+    assert len(set(seeds.tolist())) == len(seeds)
+    for _ in range(2):
+        n_id, bs, adjs = sampler.sample(torch.from_numpy(seeds))
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, sizes)
+        assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+        for adj, (o_ei, o_size) in zip(adjs, o_adjs):
+            assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)

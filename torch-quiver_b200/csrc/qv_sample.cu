@@ -98,8 +98,25 @@ constexpr unsigned long long kValueMask = (1ull << 62) - 1;
 // their tile happens to be scheduled.  Same work, same results; list overflow or no list = regular schedule.
 constexpr int kHeavyCap = 64;                    // listed warps per launch
 constexpr int kHeavyDraws = 48;                  // draws per lane that make a row "heavy" (deg - k > 32 * kHeavyDraws)
-constexpr int kHeavyWords = 1 + kHeavyCap;       // [0] = count, [1..] = entries; lives at the end of a scan region
 constexpr int kHeavyBlocks = kHeavyCap / 4;      // worker blocks: one listed warp per physical warp
+// Chain splitting for "mega" rows.  A row with c draws per lane keeps its warp busy for c dependent generator steps (a
+// 142 k-degree row: 4460 steps, 61 us alone, ~100 us next to other warps).  The reference's streams cannot be reassigned,
+// but XORWOW is linear over GF(2): lane l's state after n draws is A^n * state (xorwow_jump), so the chain is cut into
+// segments of kMegaSeg draws whose start states are computed directly; front-of-grid worker warps run the segments, the
+// hits meet in a global reservoir through the same commutative atomicMax, and the owner warp jumps its own generators
+// over the row and collects the result at write-out time.  Bit-identical to walking the chain.
+constexpr int kMegaCap = 8;       // mega rows per launch (more: the rest is walked the ordinary way)
+constexpr int kMegaDraws = 1024;  // draws per lane that make a row "mega" (deg - k > 32 * kMegaDraws)
+constexpr int kMegaSeg = 256;     // draws per lane per segment
+constexpr int kMegaBlocks = 16;   // worker blocks (4 segment-warps each)
+constexpr int64_t kMegaMaxDeg = int64_t(1) << 28;  // beyond that the 24-bit jump counter could overflow
+// auxiliary words at the end of a scan region (all zeroed with it):
+constexpr int kAuxHeavyCount = 0, kAuxHeavyList = 1;                        // [1 .. 1+kHeavyCap)
+constexpr int kAuxMegaCount = kAuxHeavyList + kHeavyCap;                     // 65
+constexpr int kAuxMegaList = kAuxMegaCount + 1;                              // (row, degree) pairs
+constexpr int kAuxMegaDone = kAuxMegaList + 2 * kMegaCap;                    // finished segments per mega row
+constexpr int kAuxMegaSlots = kAuxMegaDone + kMegaCap;                       // kMegaCap x 32 uint32 reservoirs
+constexpr int kHeavyWords = kAuxMegaSlots + kMegaCap * 16;                   // total
 
 struct ScanState {
     unsigned long long *words;  // [0] = ticket, [1 + tile] = descriptor; zeroed before each launch
@@ -223,10 +240,18 @@ __device__ __forceinline__ MapWord map_word(unsigned int epoch_hi, unsigned int 
 }
 
 // Row r belongs to warp (r & 3) of tile (r >> 6) in the reference geometry (cuda_random.cu.hpp:17-20).
-__device__ __forceinline__ void note_heavy_row(unsigned long long *heavy, int64_t r)
+__device__ __forceinline__ void note_heavy_row(unsigned long long *heavy, int64_t r, int64_t deg, int64_t k, int mega_on)
 {
-    const unsigned long long at = atomicAdd(heavy, 1ull);
-    if (at < kHeavyCap) heavy[1 + at] = (static_cast<unsigned long long>(r >> 6) << 2) | static_cast<unsigned long long>(r & 3);
+    const unsigned long long at = atomicAdd(heavy + kAuxHeavyCount, 1ull);
+    if (at < kHeavyCap)
+        heavy[kAuxHeavyList + at] = (static_cast<unsigned long long>(r >> 6) << 2) | static_cast<unsigned long long>(r & 3);
+    if (mega_on && deg - k > 32 * kMegaDraws && deg < kMegaMaxDeg) {
+        const unsigned long long m = atomicAdd(heavy + kAuxMegaCount, 1ull);
+        if (m < kMegaCap) {
+            heavy[kAuxMegaList + 2 * m] = static_cast<unsigned long long>(r);
+            heavy[kAuxMegaList + 2 * m + 1] = static_cast<unsigned long long>(deg);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -237,7 +262,7 @@ __global__ void __launch_bounds__(kScanThreads)
                       int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k, int64_t *__restrict__ counts,
                       int64_t *__restrict__ out_ptr, int64_t *__restrict__ d_total, ScanState st, int n_tiles,
                       const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
-                      int64_t *__restrict__ d_err, unsigned long long *__restrict__ heavy)
+                      int64_t *__restrict__ d_err, unsigned long long *__restrict__ heavy, int mega_on)
 {
     pdl_wait();
     pdl_release();
@@ -254,13 +279,13 @@ __global__ void __launch_bounds__(kScanThreads)
             if (cached_deg) {  // hop >= 1 of a fused k-hop: the frontier's degrees were recorded when its nodes joined
                 const int64_t deg = cached_deg[i];
                 v = (k >= 0 && deg > k) ? k : deg;
-                if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i);
+                if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i, deg, k, mega_on);
             } else {
                 const int64_t node = seeds[i];
                 if (node >= 0 && node < n_nodes) {
                     const int64_t deg = indptr[node + 1] - indptr[node];
                     v = (k >= 0 && deg > k) ? k : deg;
-                    if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i);
+                    if (heavy && deg - k > 32 * kHeavyDraws) note_heavy_row(heavy, i, deg, k, mega_on);
                     if (node_map)  // hop 0: seeds enter the node map
                         atomicMin(&node_map[node], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(i)));
                 } else if (node_map) {
@@ -412,6 +437,90 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   * the ids to emit (verbatim rows and chosen positions alike) are handled as ONE flat list of <= 16*k entries per
 //     warp -- 32 lanes wide instead of k lanes wide -- fetched with cp.async into a staging tile (verbatim rows before
 //     the generator loop even starts) and written out after a single wait.
+__device__ __forceinline__ int64_t row_degree(int64_t r, const int64_t *__restrict__ cached_deg,
+                                              const int64_t *__restrict__ seeds, const int64_t *__restrict__ indptr,
+                                              int64_t n_nodes)
+{
+    if (cached_deg) return cached_deg[r];
+    const int64_t node = seeds[r];
+    return (node >= 0 && node < n_nodes) ? indptr[node + 1] - indptr[node] : 0;
+}
+
+// by value in, by value out: taking the generator's address would give it a home in local memory for the whole kernel
+__device__ __noinline__ Xorwow xorwow_jump_dev(Xorwow s, uint64_t n, const uint32_t *__restrict__ mats)
+{
+    xorwow_jump(s, n, mats);
+    return s;
+}
+
+// Worker side of the chain splitting (see kMegaCap): warp q of the kMegaBlocks front blocks runs segments q, q + W, ...
+// of the (row, segment) pairs of the launch's mega rows.  A segment = draws [j * kMegaSeg, (j+1) * kMegaSeg) of every
+// lane's share of the row; the lane's generator is positioned by jumping over the draws of the warp's earlier rows
+// (computed from their degrees) plus the segment offset.
+__device__ __noinline__ void mega_segments(unsigned long long *__restrict__ aux, const uint32_t *__restrict__ rng_states,
+                                           const uint32_t *__restrict__ jump_mats, const RecipTable rt, int k,
+                                           const int64_t *__restrict__ cached_deg, const int64_t *__restrict__ seeds,
+                                           const int64_t *__restrict__ indptr, int64_t n_nodes)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_mega = static_cast<int>(min(aux[kAuxMegaCount], static_cast<unsigned long long>(kMegaCap)));
+    if (n_mega == 0) return;
+    const uint32_t kk = static_cast<uint32_t>(k);
+    const unsigned long long *tab = rt.recip + 1;
+    const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
+    unsigned int *slots_g = reinterpret_cast<unsigned int *>(aux + kAuxMegaSlots);
+    constexpr int kWorkers = kMegaBlocks * kSampleWarps;
+    int pair = static_cast<int>(blockIdx.x) * kSampleWarps + static_cast<int>(threadIdx.x >> 5);
+    int base = 0;
+    for (int m = 0; m < n_mega; m++) {
+        const int64_t r = static_cast<int64_t>(aux[kAuxMegaList + 2 * m]);
+        const int64_t deg = static_cast<int64_t>(aux[kAuxMegaList + 2 * m + 1]);
+        const uint32_t c0 = static_cast<uint32_t>((deg - kk + 31) >> 5);  // lane 0 draws the most
+        const int G = static_cast<int>((c0 + kMegaSeg - 1) / kMegaSeg);
+        for (; pair < base + G; pair += kWorkers) {
+            const uint32_t j = static_cast<uint32_t>(pair - base);
+            const int64_t b = r >> 6;
+            const int w = static_cast<int>(r & 3), i = static_cast<int>((r & 63) >> 2);
+            int64_t pdeg = 0;
+            if (lane < i) pdeg = row_degree(b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps, cached_deg, seeds,
+                                            indptr, n_nodes);
+            uint64_t n_prev = 0;  // draws this lane's generator made on the warp's earlier rows
+            for (int q = 0; q < i; q++) {
+                const int64_t dd = min(__shfl_sync(0xffffffffu, pdeg, q), static_cast<int64_t>(0xffffffffu));
+                if (dd > static_cast<int64_t>(kk) + lane) n_prev += static_cast<uint64_t>((dd - kk - lane + 31) >> 5);
+            }
+            const uint32_t c_l = deg > static_cast<int64_t>(kk) + lane ? static_cast<uint32_t>((deg - kk - lane + 31) >> 5) : 0;
+            const uint32_t t0 = j * kMegaSeg, t1 = min(t0 + kMegaSeg, c_l);
+            if (t0 < t1) {
+                Xorwow g;
+                const uint32_t *p = rng_states + static_cast<size_t>(b) * kRngStateWords * kRngBlockThreads + (w * 32 + lane);
+                g.d = p[0 * kRngBlockThreads];
+                g.v0 = p[1 * kRngBlockThreads];
+                g.v1 = p[2 * kRngBlockThreads];
+                g.v2 = p[3 * kRngBlockThreads];
+                g.v3 = p[4 * kRngBlockThreads];
+                g.v4 = p[5 * kRngBlockThreads];
+                xorwow_jump(g, n_prev + t0, jump_mats);
+                unsigned int *srow = slots_g + m * 32;
+                uint32_t idx = kk + lane + 32u * t0;
+                for (uint32_t t = t0; t < t1; t++, idx += 32) {
+                    const uint32_t rr = xorwow_next(g);
+                    if (idx < tab_n) {
+                        reservoir_hit(tab[idx], rr, idx + 1, kk, idx, srow);
+                    } else {
+                        const uint32_t num = rr % (idx + 1);
+                        if (num < kk) atomicMax(&srow[num], idx);
+                    }
+                }
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(aux + kAuxMegaDone + m, 1ull);
+        }
+        base += G;
+    }
+}
+
 template <bool kShortTable, int kHub, int kMinBlocks>
 __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     sample_rows_small_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
@@ -421,7 +530,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                              const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
                              const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
                              int64_t item_base_arg, const int64_t *__restrict__ d_item_base,
-                             int64_t *__restrict__ d_err, const unsigned long long *__restrict__ heavy, int late_wait)
+                             int64_t *__restrict__ d_err, unsigned long long *__restrict__ heavy, int late_wait,
+                             const uint32_t *__restrict__ jump_mats)
 {
     // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
     // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
@@ -432,6 +542,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     __shared__ int64_t o_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint32_t deg_sh[kSampleWarps][kRowsPerWarp];
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp + 1];     // entry offset of each row inside the warp's list
+    __shared__ int8_t mega_sh[kSampleWarps][kRowsPerWarp];          // index in the launch's mega list, -1 = ordinary row
     // Programmatic dependent launch, taken one step further: the kernel in front of this one is count_scan, whose blocks
     // release their dependents only after they have themselves waited for the hop's inputs (frontier rows, sizes), so
     // those are complete when a block of this kernel starts.  What count_scan PRODUCES (out_ptr, the longest-first list)
@@ -444,18 +555,25 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     int w = wp;                       // logical warp of the reference geometry: decides rows and generator streams
     int64_t b = blockIdx.x;
     bool listed_run = false;
-    if (heavy) {  // longest-first schedule: the first kHeavyBlocks blocks run the listed (heavy) warps
-        if (blockIdx.x < kHeavyBlocks) {
-            pdl_wait();  // the list is count_scan's output
-            const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
-            const unsigned int slot = blockIdx.x * kSampleWarps + wp;
+    if (heavy) {
+        // front of the grid: [segment workers of the mega rows (only with jump matrices)] [listed heavy warps] [tiles]
+        const unsigned int first_listed = jump_mats ? kMegaBlocks : 0;
+        if (blockIdx.x < first_listed) {
+            pdl_wait();  // the lists are count_scan's output
+            mega_segments(heavy, rng_states, jump_mats, rt, k, cached_deg, seeds, indptr, n_nodes);
+            return;
+        }
+        if (blockIdx.x < first_listed + kHeavyBlocks) {  // longest-first schedule
+            pdl_wait();
+            const unsigned long long n_listed = min(heavy[kAuxHeavyCount], static_cast<unsigned long long>(kHeavyCap));
+            const unsigned int slot = (blockIdx.x - first_listed) * kSampleWarps + wp;
             if (slot >= n_listed) return;
-            const unsigned long long entry = heavy[1 + slot];
+            const unsigned long long entry = heavy[kAuxHeavyList + slot];
             b = static_cast<int64_t>(entry >> 2);
             w = static_cast<int>(entry & 3);
             listed_run = true;
         } else {
-            b = blockIdx.x - kHeavyBlocks;
+            b = blockIdx.x - first_listed - kHeavyBlocks;
         }
     }
     if (b * kSampleTile >= S) return;
@@ -477,6 +595,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     }
     // lane i < 16 owns the metadata of row i; one inclusive warp scan lays the rows' entries out back to back
     uint32_t n_entries;
+    unsigned int mega_mask = 0;  // bit i: row i is a mega row handled by the segment workers
     {
         int64_t my_start = 0, my_deg = 0, my_o = 0;
         const int64_t r = b * kSampleTile + w + static_cast<int64_t>(lane) * kSampleWarps;
@@ -496,12 +615,25 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         if (heavy && !listed_run && __any_sync(0xffffffffu, my_deg - k > 32 * kHeavyDraws)) {
             // this warp owns a heavy row: if count_scan managed to list it, a front-of-grid block is already on it
             pdl_wait();
-            const unsigned long long n_listed = min(heavy[0], static_cast<unsigned long long>(kHeavyCap));
+            const unsigned long long n_listed = min(heavy[kAuxHeavyCount], static_cast<unsigned long long>(kHeavyCap));
             const unsigned long long me = (static_cast<unsigned long long>(b) << 2) | static_cast<unsigned long long>(w);
             bool found = false;
-            for (unsigned int j = lane; j < n_listed; j += 32) found |= heavy[1 + j] == me;
+            for (unsigned int j = lane; j < n_listed; j += 32) found |= heavy[kAuxHeavyList + j] == me;
             if (__any_sync(0xffffffffu, found)) return;
         }
+        int my_mega = -1;  // is this lane's row one whose chain the segment workers walk?
+        if (jump_mats) {
+            const bool cand = my_deg - k > 32 * kMegaDraws && my_deg < kMegaMaxDeg;
+            if (__any_sync(0xffffffffu, cand)) {
+                pdl_wait();
+                const int n_mega = static_cast<int>(min(heavy[kAuxMegaCount], static_cast<unsigned long long>(kMegaCap)));
+                if (cand)
+                    for (int m = 0; m < n_mega; m++)
+                        if (heavy[kAuxMegaList + 2 * m] == static_cast<unsigned long long>(r)) my_mega = m;
+            }
+        }
+        mega_mask = __ballot_sync(0xffffffffu, my_mega >= 0);
+        if (lane < kRowsPerWarp) mega_sh[wp][lane] = static_cast<int8_t>(my_mega);
         const uint32_t cnt = static_cast<uint32_t>(my_deg <= k ? my_deg : k);
         uint32_t incl = cnt;
 #pragma unroll
@@ -539,6 +671,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         for (int i = 0; i < kRowsPerWarp; i++) {
             const uint32_t d = deg_sh[wp][i];
             uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
+
             if (kShortTable && d > kk && d <= tab_n && (d - kk + 31) >> 5 < kHub) {
                 // The common row (a few draws per lane): the test above is warp-uniform and the <= kHub-1 draws are fully
                 // unrolled and predicated, so there is no divergent loop, no per-lane trip count and no bound check on the
@@ -555,6 +688,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
             }
             if (d <= first) continue;
             uint32_t rem = (d - first + 31) >> 5, idx = first;
+            if (mega_mask && (mega_mask >> i & 1u)) {  // the workers walk this row's chain (every lane has draws): step over
+                rng = xorwow_jump_dev(rng, rem, jump_mats);
+                continue;
+            }
             if (rem >= kHub && idx + 64 * kHub < tab_n) {
                 unsigned long long M[kHub];
 #pragma unroll
@@ -615,11 +752,26 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     }
     __syncwarp();
 
+    if (mega_mask) {  // wait until every segment of this warp's mega rows has been walked
+        if (lane < kRowsPerWarp && (mega_mask >> lane & 1u)) {
+            const uint32_t c0 = (deg_sh[wp][lane] - kk + 31) >> 5;
+            const unsigned long long segments = (c0 + kMegaSeg - 1) / kMegaSeg;
+            const unsigned long long *done = heavy + kAuxMegaDone + mega_sh[wp][lane];
+            while (ld_volatile_u64(done) < segments) {
+            }
+        }
+        __syncwarp();
+    }
     // sampled rows: fetch the chosen positions; then one wait and one coalesced write-out of the whole list
     for (uint32_t e = lane; e < n_entries; e += 32) {
         const int i = rowof_w[e];
-        if (deg_sh[wp][i] > kk)
-            cp_async_8(&stage_w[e], indices + start_sh[wp][i] + slots_w[static_cast<size_t>(i) * kcap + (e - pre_sh[wp][i])]);
+        if (deg_sh[wp][i] > kk) {
+            const uint32_t j = e - pre_sh[wp][i];
+            uint32_t pos = slots_w[static_cast<size_t>(i) * kcap + j];
+            if (mega_mask && (mega_mask >> i & 1u))  // global reservoir, zero-initialised: an untouched slot keeps position j
+                pos = max(__ldcv(reinterpret_cast<const unsigned int *>(heavy + kAuxMegaSlots) + mega_sh[wp][i] * 32 + j), j);
+            cp_async_8(&stage_w[e], indices + start_sh[wp][i] + pos);
+        }
     }
     if (late_wait) {  // only now are count_scan's offsets needed
         pdl_wait();
@@ -1212,6 +1364,7 @@ struct qv_sampler {
     Buffer out_ptr;  // int64[S]      (fused path / reindex_single)
     Buffer nbr;      // int64[E]      (fused path: sampled neighbour ids)
     Buffer rng_mats;   // XORWOW skip matrices (device copy)
+    Buffer jump_mats;  // XORWOW jump matrices A^(2^i) (device copy, uploaded when a graph has mega rows)
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
@@ -1317,6 +1470,7 @@ struct HopExtras {  // fused k-hop only; all null for the standalone calls
     int64_t *d_err = nullptr;
     unsigned long long *heavy = nullptr;  // longest-first list (kHeavyWords, zeroed): filled by count_scan, read by the sampler
     int late_wait = 0;                    // the sampling kernel waits for count_scan only before its write-out
+    const uint32_t *jump_mats = nullptr;  // XORWOW jump matrices: non-null enables chain splitting of mega rows
 };
 
 int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
@@ -1328,7 +1482,7 @@ int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const 
     scan.direct = n_tiles <= resident_capacity(count_scan_kernel, s->n_sm);
     QV_CUDA(launch_chained(count_scan_kernel, n_tiles, kScanThreads, 0, st, s->indptr, s->n_nodes, seeds, S_arg, d_S, k,
                            counts, out_ptr, d_total, scan, n_tiles, x.cached_deg,
-                           x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err, x.heavy));
+                           x.cached_deg ? nullptr : x.node_map, x.epoch_hi, x.d_err, x.heavy, x.jump_mats ? 1 : 0));
     QV_CHECK_LAUNCH("count_scan_kernel");
     return QV_OK;
 }
@@ -1361,17 +1515,19 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     if (k >= 0 && k <= 32 && !(impl & 1)) {
         if (!(impl & 4))  // default: fastmod table for short rows too (measured -10 us per bench step vs plain %)
             QV_CUDA(launch_chained(sample_rows_small_kernel<true, 4, 8>,
-                                   static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)), kSampleWarps * 32,
+                                   static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0) + (x.jump_mats ? kMegaBlocks : 0)),
+                                   kSampleWarps * 32,
                                    small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
                                    static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
                                    x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err, x.heavy,
-                                   x.late_wait));
+                                   x.late_wait, x.jump_mats));
         else
-            sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0)),
+            sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0) +
+                                                                          (x.jump_mats ? kMegaBlocks : 0)),
                                                     kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
                 row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err,
-                x.heavy, 0);
+                x.heavy, 0, x.jump_mats);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
@@ -1497,6 +1653,7 @@ int qv_sampler_destroy(qv_sampler *s)
     s->out_ptr.release();
     s->nbr.release();
     s->rng_mats.release();
+    s->jump_mats.release();
     s->rng_cache.release();
     s->rng_tmp.release();
     s->recip.release();
@@ -1638,7 +1795,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
     } else {
         for (int h = 0; h < n_hops; h++) {
             QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h).words, 0, (tiles_for(bn[h]) + 2) * sizeof(unsigned long long), st));
-            QV_CUDA(cudaMemsetAsync(heavy_region(s, 2 * h), 0, sizeof(unsigned long long), st));
+            QV_CUDA(cudaMemsetAsync(heavy_region(s, 2 * h), 0, kHeavyWords * sizeof(unsigned long long), st));
             QV_CUDA(cudaMemsetAsync(scan_region(s, 2 * h + 1).words, 0,
                                     (tiles_for(bn[h] + be[h]) + 2) * sizeof(unsigned long long), st));
         }
@@ -1676,6 +1833,16 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         if (!heavy_off && !s->fast && sizes[h] >= 0 && sizes[h] <= 32 && !(impl_sw & 1) &&
             s->max_degree - sizes[h] > 32 * kHeavyDraws)
             x.heavy = heavy_region(s, 2 * h);
+        // chain splitting of mega rows (needs the jump matrices on the device; QV_MEGA=0 is the A-B switch)
+        static const bool mega_off = getenv("QV_MEGA") && getenv("QV_MEGA")[0] == '0';
+        if (x.heavy && !mega_off && s->max_degree - sizes[h] > 32 * kMegaDraws) {
+            if (!s->jump_mats.ptr) {
+                const size_t bytes = size_t(kJumpBits) * kXorwowBits * kXorwowWords * sizeof(uint32_t);
+                QV_TRY(s->jump_mats.ensure(bytes));
+                QV_CUDA(cudaMemcpy(s->jump_mats.ptr, xorwow_jump_matrices_host(), bytes, cudaMemcpyHostToDevice));
+            }
+            x.jump_mats = static_cast<const uint32_t *>(s->jump_mats.ptr);
+        }
         // count_scan directly in front of the sampling kernel (rand_seed 0: no state-fill kernel in between): overlap them
         static const bool late_off = getenv("QV_PDL_LATE") && getenv("QV_PDL_LATE")[0] == '0';
         x.late_wait = (!late_off && rand_seed == 0 && !s->fast) ? 1 : 0;

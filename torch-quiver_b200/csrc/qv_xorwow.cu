@@ -79,6 +79,27 @@ std::vector<uint32_t> build_matrices()
 }
 }  // namespace
 
+const uint32_t *xorwow_jump_matrices_host()
+{
+    static std::once_flag once;
+    static std::vector<uint32_t> mats;
+    std::call_once(once, [] {
+        auto P = std::make_unique<BitMat>();
+        for (int r = 0; r < kXorwowBits; r++) {
+            uint32_t v[kXorwowWords] = {0, 0, 0, 0, 0};
+            v[r / 32] = 1u << (r & 31);
+            step_linear(v);
+            std::memcpy(P->row[r], v, sizeof v);
+        }
+        mats.resize(size_t(kJumpBits) * kXorwowBits * kXorwowWords);
+        for (int i = 0; i < kJumpBits; i++) {
+            if (i) multiply(*P, *P, *P);  // A^(2^i)
+            std::memcpy(mats.data() + size_t(i) * kXorwowBits * kXorwowWords, P->row, sizeof P->row);
+        }
+    });
+    return mats.data();
+}
+
 const uint32_t *xorwow_subseq_matrices_host()
 {
     static std::once_flag once;

@@ -52,6 +52,42 @@ __host__ __device__ __forceinline__ Xorwow xorwow_seed(uint64_t seed)
     return s;
 }
 
+// Jump-ahead by an arbitrary number of draws.  The five xorshift words evolve linearly over GF(2): state(t+n) = A^n *
+// state(t), and the Weyl word just adds n * 362437.  `mats` holds A^(2^i), i = 0..kJumpBits-1, as [i][bit r (160)][word
+// (5)] (row r = image of basis bit r); the jump multiplies in the matrices of n's set bits.  Branch-free inner loop (an
+// AND mask per state bit) so the 32 lanes of a warp, whose states differ, execute the same instructions with uniform
+// matrix loads.  ~1.6 k instructions per set bit of n: worth it for chains of thousands of draws (hub rows), not below.
+constexpr int kJumpBits = 40;  // any jump a warp's 16 rows can add up to (15 rows x 2^32 / 32 draws)
+
+__host__ __device__ inline void xorwow_jump(Xorwow &s, uint64_t n, const uint32_t *__restrict__ mats)
+{
+    uint32_t v[kXorwowWords] = {s.v0, s.v1, s.v2, s.v3, s.v4};
+    for (int i = 0; i < kJumpBits; i++) {
+        if (!((n >> i) & 1ull)) continue;  // n is (nearly) warp-uniform: at most two values per row across the lanes
+        const uint32_t *m = mats + static_cast<size_t>(i) * kXorwowBits * kXorwowWords;
+        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+        for (int w = 0; w < kXorwowWords; w++) {
+            const uint32_t bits = v[w];
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) {
+                const uint32_t mask = 0u - ((bits >> j) & 1u);
+                const uint32_t *row = m + (w * 32 + j) * kXorwowWords;
+                r0 ^= row[0] & mask;
+                r1 ^= row[1] & mask;
+                r2 ^= row[2] & mask;
+                r3 ^= row[3] & mask;
+                r4 ^= row[4] & mask;
+            }
+        }
+        v[0] = r0; v[1] = r1; v[2] = r2; v[3] = r3; v[4] = r4;
+    }
+    s.v0 = v[0]; s.v1 = v[1]; s.v2 = v[2]; s.v3 = v[3]; s.v4 = v[4];
+    s.d += static_cast<uint32_t>(n) * 362437u;  // mod 2^32
+}
+
+// Host: A^(2^i), i < kJumpBits, in the layout xorwow_jump reads (kJumpBits * 160 * 5 words, process lifetime).
+const uint32_t *xorwow_jump_matrices_host();
+
 // Host: the 128 sub-sequence skip matrices in device layout [bit r (160)][word (5)][q (128)] (uint32).
 // Returns a pointer to a process-lifetime host array of 160*5*128 words.
 const uint32_t *xorwow_subseq_matrices_host();
