@@ -101,7 +101,7 @@ constexpr int kHeavyDraws = 48;                  // draws per lane that make a r
 constexpr int kHeavyBlocks = kHeavyCap / 4;      // worker blocks: one listed warp per physical warp
 // Chain splitting for "mega" rows.  A row with c draws per lane keeps its warp busy for c dependent generator steps (a
 // 142 k-degree row: 4460 steps, 61 us alone, ~100 us next to other warps).  The reference's streams cannot be reassigned,
-// but XORWOW is linear over GF(2): lane l's state after n draws is A^n * state (xorwow_jump), so the chain is cut into
+// but XORWOW is linear over GF(2): lane l's state after n draws is A^n * state (xorwow_jump_nib), so the chain is cut into
 // segments of kMegaSeg draws whose start states are computed directly; front-of-grid worker warps run the segments, the
 // hits meet in a global reservoir through the same commutative atomicMax, and the owner warp jumps its own generators
 // over the row and collects the result at write-out time.  Bit-identical to walking the chain.
@@ -357,6 +357,11 @@ struct RecipTable {
     unsigned int quick;  // 1: short rows take the unrolled path of sample_rows_small_kernel (0 = A-B switch)
 };
 
+// Hint: bring the line holding *p into L1.  A long row walks the reciprocal table linearly (32 consecutive entries per
+// draw step); the register ring only covers one trip ahead, which is less than an L2 round trip (mega_probe: 100 cycles per
+// draw on a 142 k-degree row instead of 27 while the walk stays inside L1).
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void reservoir_hit(unsigned long long M, uint32_t r, uint32_t m, uint32_t kk, uint32_t idx,
                                               uint32_t *slots)
 {
@@ -449,7 +454,7 @@ __device__ __forceinline__ int64_t row_degree(int64_t r, const int64_t *__restri
 // by value in, by value out: taking the generator's address would give it a home in local memory for the whole kernel
 __device__ __noinline__ Xorwow xorwow_jump_dev(Xorwow s, uint64_t n, const uint32_t *__restrict__ mats)
 {
-    xorwow_jump(s, n, mats);
+    xorwow_jump_nib(s, n, mats);
     return s;
 }
 
@@ -500,10 +505,11 @@ __device__ __noinline__ void mega_segments(unsigned long long *__restrict__ aux,
                 g.v2 = p[3 * kRngBlockThreads];
                 g.v3 = p[4 * kRngBlockThreads];
                 g.v4 = p[5 * kRngBlockThreads];
-                xorwow_jump(g, n_prev + t0, jump_mats);
+                xorwow_jump_nib(g, n_prev + t0, jump_mats);
                 unsigned int *srow = slots_g + m * 32;
                 uint32_t idx = kk + lane + 32u * t0;
                 for (uint32_t t = t0; t < t1; t++, idx += 32) {
+                    if (tab_n) prefetch_l1(tab + min(idx + 32u * 24u, tab_n - 1));  // 24 steps ahead of the use
                     const uint32_t rr = xorwow_next(g);
                     if (idx < tab_n) {
                         reservoir_hit(tab[idx], rr, idx + 1, kk, idx, srow);
@@ -699,6 +705,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                 while (true) {
                     unsigned long long N[kHub];
                     const bool more = rem >= 2 * kHub && idx + 96 * kHub < tab_n;
+                    prefetch_l1(tab + min(idx + 32u * kHub * 6u, tab_n - 1));  // six trips ahead (idx + 64 kHub < tab_n here)
                     if (more) {
 #pragma unroll
                         for (int u = 0; u < kHub; u++) N[u] = tab[idx + 32 * kHub + 32 * u];
@@ -1364,7 +1371,7 @@ struct qv_sampler {
     Buffer out_ptr;  // int64[S]      (fused path / reindex_single)
     Buffer nbr;      // int64[E]      (fused path: sampled neighbour ids)
     Buffer rng_mats;   // XORWOW skip matrices (device copy)
-    Buffer jump_mats;  // XORWOW jump matrices A^(2^i) (device copy, uploaded when a graph has mega rows)
+    Buffer jump_mats;  // XORWOW jump tables (A^(2^i) as 4-bit lookups; uploaded when a graph has mega rows)
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
@@ -1837,9 +1844,9 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         static const bool mega_off = getenv("QV_MEGA") && getenv("QV_MEGA")[0] == '0';
         if (x.heavy && !mega_off && s->max_degree - sizes[h] > 32 * kMegaDraws) {
             if (!s->jump_mats.ptr) {
-                const size_t bytes = size_t(kJumpBits) * kXorwowBits * kXorwowWords * sizeof(uint32_t);
+                const size_t bytes = kJumpTableWords * sizeof(uint32_t);  // the 4-bit lookup form of A^(2^i)
                 QV_TRY(s->jump_mats.ensure(bytes));
-                QV_CUDA(cudaMemcpy(s->jump_mats.ptr, xorwow_jump_matrices_host(), bytes, cudaMemcpyHostToDevice));
+                QV_CUDA(cudaMemcpy(s->jump_mats.ptr, xorwow_jump_tables_host(), bytes, cudaMemcpyHostToDevice));
             }
             x.jump_mats = static_cast<const uint32_t *>(s->jump_mats.ptr);
         }

@@ -100,6 +100,27 @@ const uint32_t *xorwow_jump_matrices_host()
     return mats.data();
 }
 
+const uint32_t *xorwow_jump_tables_host()
+{
+    static std::once_flag once;
+    static std::vector<uint32_t> tabs;
+    std::call_once(once, [] {
+        const uint32_t *mats = xorwow_jump_matrices_host();
+        tabs.assign(kJumpTableWords, 0u);
+        for (int i = 0; i < kJumpBits; i++) {
+            const uint32_t *m = mats + size_t(i) * kXorwowBits * kXorwowWords;
+            for (int q = 0; q < kJumpNibbles; q++)
+                for (int x = 0; x < 16; x++) {
+                    uint32_t *e = tabs.data() + ((size_t(i) * kJumpNibbles + q) * 16 + x) * kJumpEntryWords;
+                    for (int bit = 0; bit < 4; bit++)
+                        if (x >> bit & 1)
+                            for (int k = 0; k < kXorwowWords; k++) e[k] ^= m[size_t(q * 4 + bit) * kXorwowWords + k];
+                }
+        }
+    });
+    return tabs.data();
+}
+
 const uint32_t *xorwow_subseq_matrices_host()
 {
     static std::once_flag once;
