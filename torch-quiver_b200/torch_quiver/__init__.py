@@ -212,6 +212,10 @@ class Quiver:
             if torch.cuda.current_device() != self.device:
                 raise RuntimeError("sample_khop(gather=...) must run with the sampler's device current")
             table, dtype, row_shape, row_bytes = store._gather_plan(self.device)
+            if max(n_id_cap, 1) * row_bytes > _FUSED_GATHER_MAX_BYTES:
+                # the output is sized for the STATIC frontier bound (the real size is not known when the gather is
+                # enqueued); beyond this the two separate calls, which allocate exactly, are the better trade
+                raise Unsupported(_lib.QV_ERR_UNSUPPORTED, "fused gather buffer would exceed QUIVER_B200_FUSED_GATHER_MAX")
             order_ptr = c_void_p(0)
             if feature_order is not None:
                 order_ptr = _ptr(_check_long_cuda(feature_order, "feature_order", self.device))
@@ -250,6 +254,7 @@ _ELEMENT_DTYPE = {1: torch.uint8, 2: torch.float16, 4: torch.float32, 8: torch.f
 
 import os as _os
 
+_FUSED_GATHER_MAX_BYTES = int(_os.environ.get("QUIVER_B200_FUSED_GATHER_MAX", str(8 << 30)))
 _PITCH_ALIGN = int(_os.environ.get("QUIVER_B200_PITCH_ALIGN", "16"))  # bytes; 64 aligns rows to DRAM access granules
 
 
