@@ -355,6 +355,7 @@ struct RecipTable {
     const unsigned long long *recip;  // [n]; recip[0] = recip[1] = 0
     unsigned int n;
     unsigned int quick;  // 1: short rows take the unrolled path of sample_rows_small_kernel (0 = A-B switch)
+    unsigned int limit;  // divisors >= limit bypass the table in sample_rows_small_kernel (experiment switch)
 };
 
 // Hint: bring the line holding *p into L1.  A long row walks the reciprocal table linearly (32 consecutive entries per
@@ -471,8 +472,6 @@ __device__ __noinline__ void mega_segments(unsigned long long *__restrict__ aux,
     const int n_mega = static_cast<int>(min(aux[kAuxMegaCount], static_cast<unsigned long long>(kMegaCap)));
     if (n_mega == 0) return;
     const uint32_t kk = static_cast<uint32_t>(k);
-    const unsigned long long *tab = rt.recip + 1;
-    const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
     unsigned int *slots_g = reinterpret_cast<unsigned int *>(aux + kAuxMegaSlots);
     constexpr int kWorkers = kMegaBlocks * kSampleWarps;
     int pair = static_cast<int>(blockIdx.x) * kSampleWarps + static_cast<int>(threadIdx.x >> 5);
@@ -508,15 +507,12 @@ __device__ __noinline__ void mega_segments(unsigned long long *__restrict__ aux,
                 xorwow_jump_nib(g, n_prev + t0, jump_mats);
                 unsigned int *srow = slots_g + m * 32;
                 uint32_t idx = kk + lane + 32u * t0;
+                // plain `%` here: ncu put 43 % of this launch's samples on the wait for the reciprocal-table load (each
+                // segment streams through its own cold 64 KB of the table, one load in flight); a handful of warps do
+                // not saturate the XU pipe the table was introduced to relieve
                 for (uint32_t t = t0; t < t1; t++, idx += 32) {
-                    if (tab_n) prefetch_l1(tab + min(idx + 32u * 24u, tab_n - 1));  // 24 steps ahead of the use
-                    const uint32_t rr = xorwow_next(g);
-                    if (idx < tab_n) {
-                        reservoir_hit(tab[idx], rr, idx + 1, kk, idx, srow);
-                    } else {
-                        const uint32_t num = rr % (idx + 1);
-                        if (num < kk) atomicMax(&srow[num], idx);
-                    }
+                    const uint32_t num = xorwow_next(g) % (idx + 1);
+                    if (num < kk) atomicMax(&srow[num], idx);
                 }
             }
             __threadfence();
@@ -673,7 +669,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         const uint32_t first = kk + lane;
         const bool quick_rows = rt.quick != 0;
         const unsigned long long *tab = rt.recip + 1;  // tab[idx] = recip[idx + 1]
-        const uint32_t tab_n = rt.n > 0 ? rt.n - 1 : 0;
+        // rt.limit (QV_TAB_LIMIT, default: none) can cut the table short so that long walks fall back to `%`.  Measured:
+        // with an 8192-entry limit a 142 k-degree row got 2x SLOWER (540 -> 1150 us in mega_probe with QV_MEGA=0) and the
+        // 64 k-seed batch collapsed (8.8 -> 1.0 G SEPS): cold table loads are still cheaper than the divergent `%` loop.
+        const uint32_t tab_n = rt.n > 0 ? min(rt.n - 1, rt.limit) : 0;
         for (int i = 0; i < kRowsPerWarp; i++) {
             const uint32_t d = deg_sh[wp][i];
             uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
@@ -1516,7 +1515,9 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
     const int64_t blocks = (S_bound + kSampleTile - 1) / kSampleTile;
     QV_REQUIRE(blocks < (int64_t(1) << 31), "sample: too many seeds (%lld)", (long long)S_bound);
     static const bool quick_off = getenv("QV_SAMPLE_QUICK") && getenv("QV_SAMPLE_QUICK")[0] == '0';
-    const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n, quick_off ? 0u : 1u};
+    static const unsigned int tab_limit = getenv("QV_TAB_LIMIT") ? static_cast<unsigned int>(atoll(getenv("QV_TAB_LIMIT")))
+                                                                    : 0xFFFFFFFFu;  // no limit
+    const RecipTable rt{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n, quick_off ? 0u : 1u, tab_limit};
     static const int impl = getenv("QV_SAMPLE_IMPL") ? atoi(getenv("QV_SAMPLE_IMPL")) : 0;  // tuning switch
     const size_t small_smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max<int64_t>(k, 1) * 13;
     if (k >= 0 && k <= 32 && !(impl & 1)) {
