@@ -6,6 +6,11 @@
                     (oracle/_ref/torch_quiver_ref*.so; quiver.cpp:21-84): counts, verbatim rows (deg <= k),
                     reindex_single results, and one complete (unseeded) reference draw per graph that the structural
                     validator must accept.
+  gpu_path_kat.json frozen outputs of the GPU-path restatement (oracle/qv_oracle.c: CSRRowWiseSampleKernel's generator
+                    assignment + first-occurrence reindex, cuda_random.cu.hpp:7-69, quiver_sample.cu:18-63) for whole
+                    k-hop samples, rand_seed 0.  NOT produced by the reference (its GPU build cannot run here and its
+                    tests store no sampled ids): it freezes the oracle, which the two files above pin, so that neither a
+                    kernel change nor an oracle change can move the sampled ids unnoticed.
 Usage: python tests/golden/make_golden.py   (needs `make -C oracle all ref` first; /root/reference is NOT needed at
 test time -- the tests read only the JSON files written here.)
 """
@@ -60,6 +65,25 @@ def ref_cpu():
     print("ref_cpu_kat.json:", len(cases), "cases")
 
 
+def gpu_path():
+    cases = []
+    for name, (n, mean, seed, S, sizes) in {
+            "two_tiles": (500, 14.0, 21, 70, [5, 3]),          # 70 seeds: crosses the 64-row tile boundary
+            "three_hops": (800, 20.0, 22, 40, [15, 10, 5]),    # the bench fan-out
+            "wide_first_hop": (400, 30.0, 23, 33, [25, 10]),   # the Reddit fan-out (config 0)
+    }.items():
+        indptr, indices = powerlaw_csr(n, mean, seed=seed)
+        seeds = np.random.default_rng(seed).permutation(n)[:S].astype(np.int64)
+        n_id, bs, adjs = oracle.khop(indptr, indices, seeds, sizes)
+        cases.append(dict(name=name, graph=dict(n_nodes=n, mean_deg=mean, seed=seed), seeds=seeds.tolist(), sizes=sizes,
+                          n_id=n_id.tolist(),
+                          adjs=[dict(edge_index=ei.tolist(), size=list(map(int, size))) for ei, size in adjs]))
+    json.dump({"source": "oracle/qv_oracle.c GPU-path restatement, rand_seed 0 (see make_golden.py docstring)",
+               "cases": cases}, open(os.path.join(HERE, "gpu_path_kat.json"), "w"))
+    print("gpu_path_kat.json:", len(cases), "cases")
+
+
 if __name__ == "__main__":
     xorwow()
     ref_cpu()
+    gpu_path()

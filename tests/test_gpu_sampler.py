@@ -556,3 +556,22 @@ def test_mega_rows_chain_splitting_is_bit_exact(oracle, n_mega, sizes):
         assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
         for adj, (o_ei, o_size) in zip(adjs, o_adjs):
             assert torch.equal(adj.edge_index.cpu(), torch.from_numpy(o_ei)) and adj.size.tolist() == list(o_size)
+
+
+def test_khop_against_committed_golden_vectors(golden_dir):
+    """GPU k-hop vs tests/golden/gpu_path_kat.json -- stored vectors, no oracle involved at run time."""
+    import json
+    import os
+    import quiver
+    kat = json.load(open(os.path.join(golden_dir, "gpu_path_kat.json")))
+    for c in kat["cases"]:
+        g = c["graph"]
+        indptr, indices = powerlaw_csr(g["n_nodes"], g["mean_deg"], seed=g["seed"])
+        topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+        for fused in (True, False):
+            sampler = quiver.pyg.GraphSageSampler(topo, c["sizes"], device=0, mode="GPU")
+            sampler.fused = fused
+            n_id, bs, adjs = sampler.sample(torch.tensor(c["seeds"]))
+            assert n_id.cpu().tolist() == c["n_id"] and bs == len(c["seeds"]), (c["name"], fused)
+            for adj, want in zip(adjs, c["adjs"]):
+                assert adj.edge_index.cpu().tolist() == want["edge_index"] and adj.size.tolist() == want["size"]

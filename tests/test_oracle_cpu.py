@@ -163,3 +163,18 @@ def test_cal_next_oracle_formula(oracle):
                 continue
             acc *= (1 - p[u]) if deg[u] <= 3 else (1 - p[u] + p[u] * (deg[u] - 3) / deg[u])
         assert abs(cur[v] - (1 - (1 - p[v]) * acc)) < 1e-5
+
+
+def test_gpu_path_golden_khop(oracle, golden_dir):
+    """The frozen k-hop vectors (tests/golden/gpu_path_kat.json): the oracle must keep producing exactly these ids."""
+    import json
+    from graphs import powerlaw_csr
+    kat = json.load(open(os.path.join(golden_dir, "gpu_path_kat.json")))
+    assert len(kat["cases"]) >= 3
+    for c in kat["cases"]:
+        g = c["graph"]
+        indptr, indices = powerlaw_csr(g["n_nodes"], g["mean_deg"], seed=g["seed"])
+        n_id, bs, adjs = oracle.khop(indptr, indices, np.array(c["seeds"], np.int64), c["sizes"])
+        assert n_id.tolist() == c["n_id"] and bs == len(c["seeds"])
+        for (ei, size), want in zip(adjs, c["adjs"]):
+            assert ei.tolist() == want["edge_index"] and list(map(int, size)) == want["size"]
