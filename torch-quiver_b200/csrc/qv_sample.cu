@@ -427,22 +427,6 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Fan-outs up to 32 (every GraphSAGE configuration in BASELINE.json).
-//
-// Profiling the first two versions of this kernel on the products-shaped bench batch (170 k rows in the last hop) showed
-// that the reservoir draws themselves are ~1/4 of the issued instructions (1.8 warp-iterations per row on average); the
-// rest was per-row overhead -- shuffles, warp syncs, a dependent memory latency and a 5/32-lane-wide gather per row --
-// plus one SM grinding through a 29 k-degree hub row at ~250 cycles per draw long after the others had finished.
-// What parity fixes is only this: lane l owns ONE generator stream that serves the lane's draws of row 0, then row 1, ...
-// and the number of draws it makes in a row, ceil((deg - k - l) / 32), is known up front.  Hence:
-//   * the 16 reservoirs of a warp's rows are all live in shared memory, so the row loop needs NO warp synchronisation:
-//     a lane just walks its stream row after row, results meet through shared-memory atomicMax (commutative);
-//   * long runs inside one row (hubs) go 8 draws per trip with the fastmod reciprocals of the NEXT trip already in
-//     flight and all 8 generator outputs produced before the first test, so a lone warp is not serialised on one
-//     divide-and-branch latency per draw; short rows use the plain `%` (nothing to look up);
-//   * the ids to emit (verbatim rows and chosen positions alike) are handled as ONE flat list of <= 16*k entries per
-//     warp -- 32 lanes wide instead of k lanes wide -- fetched with cp.async into a staging tile (verbatim rows before
-//     the generator loop even starts) and written out after a single wait.
 __device__ __forceinline__ int64_t row_degree(int64_t r, const int64_t *__restrict__ cached_deg,
                                               const int64_t *__restrict__ seeds, const int64_t *__restrict__ indptr,
                                               int64_t n_nodes)
@@ -523,6 +507,22 @@ __device__ __noinline__ void mega_segments(unsigned long long *__restrict__ aux,
     }
 }
 
+// Fan-outs up to 32 (every GraphSAGE configuration in BASELINE.json).
+//
+// Profiling the first two versions of this kernel on the products-shaped bench batch (170 k rows in the last hop) showed
+// that the reservoir draws themselves are ~1/4 of the issued instructions (1.8 warp-iterations per row on average); the
+// rest was per-row overhead -- shuffles, warp syncs, a dependent memory latency and a 5/32-lane-wide gather per row --
+// plus one SM grinding through a 29 k-degree hub row at ~250 cycles per draw long after the others had finished.
+// What parity fixes is only this: lane l owns ONE generator stream that serves the lane's draws of row 0, then row 1, ...
+// and the number of draws it makes in a row, ceil((deg - k - l) / 32), is known up front.  Hence:
+//   * the 16 reservoirs of a warp's rows are all live in shared memory, so the row loop needs NO warp synchronisation:
+//     a lane just walks its stream row after row, results meet through shared-memory atomicMax (commutative);
+//   * long runs inside one row (hubs) go 8 draws per trip with the fastmod reciprocals of the NEXT trip already in
+//     flight and all 8 generator outputs produced before the first test, so a lone warp is not serialised on one
+//     divide-and-branch latency per draw; short rows use the plain `%` (nothing to look up);
+//   * the ids to emit (verbatim rows and chosen positions alike) are handled as ONE flat list of <= 16*k entries per
+//     warp -- 32 lanes wide instead of k lanes wide -- fetched with cp.async into a staging tile (verbatim rows before
+//     the generator loop even starts) and written out after a single wait.
 template <bool kShortTable, int kHub, int kMinBlocks>
 __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
     sample_rows_small_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
