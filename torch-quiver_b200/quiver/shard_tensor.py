@@ -1,5 +1,7 @@
 """Python-level ShardTensor: budgeted placement, cross-clique fallback, IPC plumbing.
 Reference: srcs/python/quiver/shard_tensor.py:51-213."""
+from typing import NamedTuple
+
 import torch
 
 import torch_quiver as torch_qv
@@ -7,17 +9,10 @@ import torch_quiver as torch_qv
 from .utils import Topo, parse_size
 
 
-class Offset:
-    def __init__(self, start, end):
-        self.start_, self.end_ = start, end
-
-    @property
-    def start(self):
-        return self.start_
-
-    @property
-    def end(self):
-        return self.end_
+class Offset(NamedTuple):
+    """Row range [start, end) of the logical table held by one device (reference: shard_tensor.py:8-32)."""
+    start: int
+    end: int
 
 
 class ShardTensorConfig:
@@ -50,37 +45,42 @@ class ShardTensor:
         self.topo = Topo(sorted(devices))
         self.current_clique = self.topo.get_clique_id(self.current_device)
 
-    def append(self, cpu_tensor, device):
+    def _place(self, rows, device, first_row):
+        """Hand `rows` to the C layer as the next shard (device >= 0: copied into that GPU's HBM; -1: the pinned-host tier,
+        aliased not copied) and record its logical row range."""
         if device == -1:
-            if self.cpu_tensor is not None:
-                raise Exception("cpu tensor has been already appended")
-            self.cpu_tensor = cpu_tensor
-            self.shard_tensor.append(cpu_tensor, -1)
-            return
-        if self.shard_tensor_config.device_memory_budget.get(device) is not None:
+            self.cpu_tensor = rows
+        else:
+            self.shard_tensor_config.tensor_offset_device[device] = Offset(first_row, first_row + rows.shape[0])
+        self.shard_tensor.append(rows, device)
+
+    def append(self, cpu_tensor, device):
+        """One more shard at the end of the table (reference: shard_tensor.py:74-98): at most one per GPU, one host tier."""
+        budgets = self.shard_tensor_config.device_memory_budget
+        if device == -1 and self.cpu_tensor is not None:
+            raise Exception("cpu tensor has been already appended")
+        if device != -1 and budgets.get(device) is not None:
             raise Exception(f"{device} tensor has been already appended")
-        start = self.shard_tensor.size(0)
-        self.shard_tensor_config.tensor_offset_device[device] = Offset(start, start + cpu_tensor.shape[0])
-        self.shard_tensor_config.device_memory_budget[device] = cpu_tensor.numel() * cpu_tensor.element_size()
-        self.shard_tensor.append(cpu_tensor, device)
+        if device != -1:
+            budgets[device] = cpu_tensor.numel() * cpu_tensor.element_size()
+        self._place(cpu_tensor, device, self.shard_tensor.size(0))
 
     def partition(self, tensor, memory_budget):
+        """Rows of `tensor` that fit into `memory_budget` bytes."""
         return memory_budget // (tensor.shape[1] * tensor.element_size())
 
     def from_cpu_tensor(self, tensor):
         """Fill devices in config order up to their budgets, the rest goes to the pinned-host tier
         (reference: shard_tensor.py:107-136)."""
-        cur = 0
+        total, done = tensor.shape[0], 0
         for device_id, budget in self.shard_tensor_config.device_memory_budget.items():
-            if cur > tensor.shape[0]:
+            if done > total:
                 break
-            size = min(self.partition(tensor, budget), tensor.shape[0] - cur)
-            self.shard_tensor.append(tensor[cur:cur + size], device_id)
-            self.shard_tensor_config.tensor_offset_device[device_id] = Offset(cur, cur + size)
-            cur += size
-        if cur < tensor.shape[0]:
-            self.cpu_tensor = tensor[cur:]
-            self.shard_tensor.append(self.cpu_tensor, -1)
+            take = min(self.partition(tensor, budget), total - done)
+            self._place(tensor[done:done + take], device_id, done)
+            done += take
+        if done < total:
+            self._place(tensor[done:], -1, done)
 
     def collect_device(self, input_orders, nodes, inter_device, wait_results):
         """Rows owned by a GPU outside this device's P2P clique: gather them ON that GPU, then copy

@@ -70,13 +70,16 @@ class Topo:
 
 
 def get_csr_from_coo(edge_index):
-    """COO -> CSR exactly as the reference does it (utils.py:109-116): scipy merges duplicate edges, sorts the
-    columns of each row and infers rows = max(src) + 1."""
-    from scipy.sparse import csr_matrix
-    src = edge_index[0].numpy()
-    dst = edge_index[1].numpy()
-    data = np.zeros(dst.shape, dtype=np.int32)
-    return csr_matrix((data, (src, dst)))
+    """COO -> CSR with the reference's semantics (utils.py:109-116: `scipy.sparse.csr_matrix((zeros, (row, col)))`):
+    duplicate edges are merged, the columns of each row come out sorted, and the row count is max(src) + 1 -- so a node
+    that only ever appears as a destination has no row."""
+    from scipy.sparse import coo_matrix
+    rows, cols = (edge_index[i].numpy() for i in (0, 1))
+    return coo_matrix((np.zeros(cols.shape[0], dtype=np.int32), (rows, cols))).tocsr()
+
+
+def _as_long(t):
+    return (torch.from_numpy(t) if isinstance(t, np.ndarray) else t).to(torch.long)
 
 
 class CSRTopo:
@@ -84,75 +87,54 @@ class CSRTopo:
 
     >>> csr_topo = CSRTopo(edge_index=edge_index)
     >>> csr_topo = CSRTopo(indptr=indptr, indices=indices)
+
+    `indptr`, `indices`, `eid` are read-only views of what was passed in (CPU int64 tensors); `feature_order` is filled in
+    by Feature.from_cpu_tensor when rows get re-ordered by degree.
     """
+    _SHARED = ("indptr_", "indices_", "eid_", "feature_order_")
 
     def __init__(self, edge_index=None, indptr=None, indices=None, eid=None):
         if edge_index is not None:
-            m = get_csr_from_coo(edge_index)
-            self.indptr_ = torch.from_numpy(m.indptr).type(torch.long)
-            self.indices_ = torch.from_numpy(m.indices).type(torch.long)
-        elif indptr is not None and indices is not None:
-            if isinstance(indptr, np.ndarray):
-                indptr, indices = torch.from_numpy(indptr), torch.from_numpy(indices)
-            self.indptr_ = indptr.type(torch.long)
-            self.indices_ = indices.type(torch.long)
-        else:
+            csr = get_csr_from_coo(edge_index)
+            indptr, indices = csr.indptr, csr.indices
+        elif indptr is None or indices is None:
             raise ValueError("CSRTopo needs edge_index or (indptr, indices)")
+        self.indptr_, self.indices_ = _as_long(indptr), _as_long(indices)
         self.eid_ = eid
         self.feature_order_ = None
 
-    @property
-    def indptr(self):
-        return self.indptr_
-
-    @property
-    def indices(self):
-        return self.indices_
-
-    @property
-    def eid(self):
-        return self.eid_
+    indptr = property(lambda self: self.indptr_)
+    indices = property(lambda self: self.indices_)
+    eid = property(lambda self: self.eid_)
+    degree = property(lambda self: torch.diff(self.indptr_))
+    node_count = property(lambda self: self.indptr_.numel() - 1)
+    edge_count = property(lambda self: self.indices_.numel())
 
     @property
     def feature_order(self):
         return self.feature_order_
 
     @feature_order.setter
-    def feature_order(self, feature_order):
-        self.feature_order_ = feature_order
-
-    @property
-    def degree(self):
-        return self.indptr[1:] - self.indptr[:-1]
-
-    @property
-    def node_count(self):
-        return self.indptr_.shape[0] - 1
-
-    @property
-    def edge_count(self):
-        return self.indices_.shape[0]
+    def feature_order(self, order):
+        self.feature_order_ = order
 
     def share_memory_(self):
-        self.indptr_.share_memory_()
-        self.indices_.share_memory_()
-        if self.eid_ is not None:
-            self.eid_.share_memory_()
-        if self.feature_order_ is not None:
-            self.feature_order_.share_memory_()
+        for name in self._SHARED:
+            t = getattr(self, name)
+            if t is not None:
+                t.share_memory_()
 
 
 def reindex_by_config(adj_csr: CSRTopo, graph_feature, gpu_portion):
     """Degree-descending row order with the hot `gpu_portion` prefix shuffled so clique shards are load balanced
     (reference: utils.py:229-241).  Returns (permuted feature, new_order) with feature_new[new_order[i]] == feature[i]."""
-    node_count = adj_csr.indptr.shape[0] - 1
-    hot = int(node_count * gpu_portion)
-    degree = adj_csr.indptr[1:] - adj_csr.indptr[:-1]
-    _, prev_order = torch.sort(degree, descending=True)
-    prev_order[:hot] = prev_order[torch.randperm(hot)]
-    new_order = torch.zeros_like(prev_order)
-    new_order[prev_order] = torch.arange(node_count, dtype=torch.long)
-    return graph_feature[prev_order], new_order
+    n = adj_csr.node_count
+    by_degree = torch.argsort(adj_csr.degree, descending=True, stable=False)
+    hot = int(n * gpu_portion)
+    by_degree[:hot] = by_degree[:hot][torch.randperm(hot)]
+    inverse = torch.empty_like(by_degree)
+    inverse[by_degree] = torch.arange(n, dtype=torch.long)
+    return graph_feature[by_degree], inverse
 
 
 def reindex_feature(graph: CSRTopo, feature, ratio):
