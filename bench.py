@@ -519,6 +519,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with printf on
+    # the first communicator), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a
+    # private duplicate of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         res = run_reference(args, rank, world)
     else:
@@ -531,7 +537,9 @@ def main():
             import torch.distributed as dist
             dist.destroy_process_group()
     if res is not None:
-        print(json.dumps(res))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(res) + "\n").encode())
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":
