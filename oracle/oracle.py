@@ -37,6 +37,8 @@ def _load():
     lib.qo_sample_counts.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp]
     lib.qo_sample_neighbor_gpu.restype = None
     lib.qo_sample_neighbor_gpu.argtypes = [u64, i64, i64, vp, vp, vp, vp, vp]
+    lib.qo_sample_neighbor_gpu_split.restype = None
+    lib.qo_sample_neighbor_gpu_split.argtypes = [u64, i64, i64, vp, vp, vp, vp, vp, i64, i64]
     lib.qo_reindex.restype = i64
     lib.qo_reindex.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp]
     lib.qo_gather.restype = None
@@ -95,6 +97,17 @@ def sample_neighbor(indptr, indices, seeds, k, rand_seed=0):
     out = np.zeros(tot, np.int64)
     _lib.qo_sample_neighbor_gpu(int(rand_seed), int(k), seeds.shape[0], _p(seeds), _p(indptr), _p(indices), _p(out_ptr),
                                 _p(out))
+    return out, counts
+
+
+def sample_neighbor_split(indptr, indices, seeds, k, mega_draws, seg, rand_seed=0):
+    """sample_neighbor with the chains of rows above `mega_draws` draws per lane cut into independent `seg`-draw segments
+    positioned by offset skip-ahead (qo_sample_neighbor_gpu_split): must equal sample_neighbor exactly."""
+    indptr, indices, seeds = _i64(indptr), _i64(indices), _i64(seeds)
+    counts, out_ptr, tot = sample_counts(indptr, seeds, k)
+    out = np.zeros(tot, np.int64)
+    _lib.qo_sample_neighbor_gpu_split(int(rand_seed), int(k), seeds.shape[0], _p(seeds), _p(indptr), _p(indices),
+                                      _p(out_ptr), _p(out), int(mega_draws), int(seg))
     return out, counts
 
 

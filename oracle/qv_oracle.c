@@ -231,6 +231,85 @@ QO_API void qo_sample_neighbor_gpu(uint64_t rand_seed, int64_t k, int64_t S, con
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * The same sampler with the generator chains of long rows CUT INTO SEGMENTS -- an executable statement of why the
+ * product's "mega row" path (torch-quiver_b200/csrc/qv_sample.cu: mega_segments) is bit-identical to the walk above.
+ * A lane's stream is a function of how many draws it has made: state(n) = curand_init(seed, subsequence, offset = n)
+ * (curand_kernel.h:820, the offset skip-ahead).  So for a row with more than `mega_draws` draws per lane
+ *   - the draws of lane l, t in [0, c_l), c_l = ceil((deg - k - l) / 32), are grouped into segments of `seg` draws;
+ *   - segment j of lane l starts from state(n_prev_l + j*seg), where n_prev_l counts the lane's draws on the warp's
+ *     earlier rows -- no state is carried from one segment to the next, segments may run in any order;
+ *   - hits go to slots by max (commutative), slots start at 0 and an untouched slot j reads as j (what the kernel's
+ *     zero-initialised global reservoir does);
+ *   - after the row the lane continues from state(n_prev_l + c_l).
+ * Segments are deliberately evaluated in REVERSE order here.
+ * ---------------------------------------------------------------------------------------------- */
+QO_API void qo_sample_neighbor_gpu_split(uint64_t rand_seed, int64_t k, int64_t S, const int64_t *seeds,
+                                         const int64_t *indptr, const int64_t *indices, const int64_t *out_ptr,
+                                         int64_t *out, int64_t mega_draws, int64_t seg)
+{
+    const int BLOCK_WARPS = 4, TILE = 64, WARP = 32;
+    const int64_t grid = (S + TILE - 1) / TILE;
+    int64_t *slots = (int64_t *)malloc(sizeof(int64_t) * (size_t)(k > 0 ? k : 1));
+    for (int64_t b = 0; b < grid; b++) {
+        const int64_t last_row = ((b + 1) * TILE < S) ? (b + 1) * TILE : S;
+        const uint64_t seed = rand_seed * (uint64_t)grid + (uint64_t)b;
+        for (int w = 0; w < BLOCK_WARPS; w++) {
+            uint64_t made[32]; /* draws made so far by each lane's generator */
+            qo_xorwow rng[32];
+            for (int l = 0; l < WARP; l++) {
+                made[l] = 0;
+                qo_xorwow_init(seed, (uint64_t)(w * WARP + l), 0, &rng[l]);
+            }
+            for (int64_t out_row = b * TILE + w; out_row < last_row; out_row += BLOCK_WARPS) {
+                const int64_t row = seeds[out_row];
+                const int64_t start = indptr[row];
+                const int64_t deg = indptr[row + 1] - start;
+                const int64_t o = out_ptr[out_row];
+                if (deg <= k) {
+                    for (int64_t j = 0; j < deg; j++) out[o + j] = indices[start + j];
+                    continue;
+                }
+                const int64_t c0 = (deg - k + WARP - 1) / WARP; /* lane 0 draws the most */
+                if (c0 <= mega_draws) { /* ordinary row: walk it */
+                    for (int64_t j = 0; j < k; j++) slots[j] = j;
+                    for (int l = 0; l < WARP; l++)
+                        for (int64_t idx = k + l; idx < deg; idx += WARP) {
+                            const uint32_t num = qo_xorwow_next(&rng[l]) % (uint32_t)(idx + 1);
+                            made[l]++;
+                            if ((int64_t)num < k && slots[num] < idx) slots[num] = idx;
+                        }
+                    for (int64_t j = 0; j < k; j++) out[o + j] = indices[start + slots[j]];
+                    continue;
+                }
+                /* mega row: independent segments, last one first */
+                for (int64_t j = 0; j < k; j++) slots[j] = 0;
+                const int64_t n_seg = (c0 + seg - 1) / seg;
+                for (int64_t sj = n_seg - 1; sj >= 0; sj--)
+                    for (int l = 0; l < WARP; l++) {
+                        const int64_t c_l = deg > k + l ? (deg - k - l + WARP - 1) / WARP : 0;
+                        const int64_t t0 = sj * seg, t1 = (t0 + seg < c_l) ? t0 + seg : c_l;
+                        if (t0 >= t1) continue;
+                        qo_xorwow g;
+                        qo_xorwow_init(seed, (uint64_t)(w * WARP + l), made[l] + (uint64_t)t0, &g);
+                        for (int64_t t = t0; t < t1; t++) {
+                            const int64_t idx = k + l + WARP * t;
+                            const uint32_t num = qo_xorwow_next(&g) % (uint32_t)(idx + 1);
+                            if ((int64_t)num < k && slots[num] < idx) slots[num] = idx;
+                        }
+                    }
+                for (int l = 0; l < WARP; l++) { /* the owner steps over the row */
+                    const int64_t c_l = deg > k + l ? (deg - k - l + WARP - 1) / WARP : 0;
+                    made[l] += (uint64_t)c_l;
+                    qo_xorwow_init(seed, (uint64_t)(w * WARP + l), made[l], &rng[l]);
+                }
+                for (int64_t j = 0; j < k; j++) out[o + j] = indices[start + (slots[j] > j ? slots[j] : j)];
+            }
+        }
+    }
+    free(slots);
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Reindex: frontier = unique(concat(inputs, outputs)) in first-occurrence order; col_idx[e] = local id of
  * outputs[e]; row_idx[e] = position of the seed that produced e.
  * GPU semantics (duplicate seeds are merged): quiver_sample.cu:18-63 (FillWithDuplicates: min index wins,

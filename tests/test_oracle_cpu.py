@@ -178,3 +178,24 @@ def test_gpu_path_golden_khop(oracle, golden_dir):
         assert n_id.tolist() == c["n_id"] and bs == len(c["seeds"])
         for (ei, size), want in zip(adjs, c["adjs"]):
             assert ei.tolist() == want["edge_index"] and list(map(int, size)) == want["size"]
+
+
+@pytest.mark.parametrize("mega_draws,seg", [(0, 1), (2, 3), (8, 4), (64, 256)])
+def test_chain_splitting_equals_the_sequential_walk(oracle, mega_draws, seg):
+    """Executable statement of the product's mega-row scheme (qo_sample_neighbor_gpu_split): cutting a lane's generator
+    chain into segments positioned by offset skip-ahead, evaluated in reverse order and merged by max, gives exactly the
+    sequential reservoir walk -- for every threshold / segment length, several long rows per warp, rows at the end of a
+    warp's list, k = 1 .. 32."""
+    rng = np.random.default_rng(7)
+    n = 3000
+    deg = rng.integers(0, 40, n)
+    deg[rng.permutation(n)[:25]] = rng.integers(2000, 9000, 25)
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, n, int(indptr[-1])).astype(np.int64)
+    heavy = np.flatnonzero(deg >= 2000)
+    seeds = np.concatenate([heavy[:12], rng.permutation(n)[:150], heavy[12:]]).astype(np.int64)
+    for k in (1, 5, 15, 32):
+        want, want_cnt = oracle.sample_neighbor(indptr, indices, seeds, k)
+        got, got_cnt = oracle.sample_neighbor_split(indptr, indices, seeds, k, mega_draws, seg)
+        assert np.array_equal(got_cnt, want_cnt) and np.array_equal(got, want), (k, mega_draws, seg)
