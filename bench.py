@@ -166,6 +166,27 @@ def reference_cpu_step(ref, seeds, x_cpu):
     return edges, rows.shape[0], t1 - t0, t2 - t1
 
 
+def cpu_baseline_sample(indptr_cpu, indices_cpu, batches_host, warmup, x_cpu, row_bytes, n_b=4):
+    """The `cpu_baseline` object of the N=1 line: the reference's CPU path timed on a bounded sample (n_b batches of the
+    same workload, ~2 s of CPU work) on this box's host cores."""
+    ref = reference_cpu_setup(indptr_cpu, indices_cpu)
+    e = r = 0
+    ts = tg = 0.0
+    reference_cpu_step(ref, batches_host[0], x_cpu)
+    t0 = time.perf_counter()
+    for b in batches_host[warmup:warmup + n_b]:
+        ee, rr, a, gg = reference_cpu_step(ref, b, x_cpu)
+        e, r, ts, tg = e + ee, r + rr, ts + a, tg + gg
+    tt = time.perf_counter() - t0
+    what = ("reference CPU extension compiled from its sources (as shipped: serial at::parallel_for)"
+            if ref["kind"] == "reference" else "oracle/qv_oracle.c port, 1 core (oracle/_ref not built)")
+    return {"value": e / tt, "unit": "edges/s", "cores": torch.get_num_threads() if ref["openmp"] else 1,
+            "kind": ref["kind"],
+            "sample": f"{n_b} batches of the same workload; {what} for sample+reindex, torch CPU gather on "
+                      f"{torch.get_num_threads()} threads; host has {os.cpu_count()} cores",
+            "seps_sampler_only": e / ts, "feature_gather_GiBps": r * row_bytes / tg / 2**30}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return None
@@ -499,30 +520,7 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "measured peer-copy 770 GB/s per direction (B200_PROFILING.md)",
                          "remote_row_fraction": remote_frac}
     if world == 1 and not args.no_cpu_baseline:
-        ref = reference_cpu_setup(indptr_cpu, indices_cpu)
-        if ref is not None:
-            n_b = 4
-            e = r = 0
-            ts = tg = 0.0
-            reference_cpu_step(ref, batches_host[0], x_cpu)
-            t0 = time.perf_counter()
-            for b in batches_host[args.warmup:args.warmup + n_b]:
-                ee, rr, a, gg = reference_cpu_step(ref, b, x_cpu)
-                e, r, ts, tg = e + ee, r + rr, ts + a, tg + gg
-            tt = time.perf_counter() - t0
-            out["cpu_baseline"] = {
-                "value": e / tt, "unit": "edges/s", "cores": 1 if not ref["openmp"] else torch.get_num_threads(),
-                "kind": ref["kind"],
-                "sample": f"{n_b} batches of the same workload; "
-                          + ("reference CPU extension compiled from its sources " if ref["kind"] == "reference"
-                             else "oracle/qv_oracle.c port (oracle/_ref not built) ")
-                          + ("(1 core) " if ref["kind"] == "port" else "(as shipped: serial at::parallel_for) ")
-                          + f"for sample+reindex, torch CPU gather on "
-                          f"{torch.get_num_threads()} threads; host has {os.cpu_count()} cores",
-                "seps_sampler_only": e / ts, "feature_gather_GiBps": r * row_bytes / tg / 2**30}
-        else:
-            out["cpu_baseline"] = {"value": None, "unit": "edges/s", "cores": 0, "kind": "reference",
-                                   "sample": "oracle/_ref not built"}
+        out["cpu_baseline"] = cpu_baseline_sample(indptr_cpu, indices_cpu, batches_host, args.warmup, x_cpu, row_bytes)
     return out
 
 
