@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QV_ABI_VERSION 1
+#define QV_ABI_VERSION 2 /* 2: edge-id outputs (qv_sample_fill / qv_khop / qv_khop_gather), qv_copy_rows_device */
 #define QV_MAX_SHARDS 16 /* 8 GPU shards + pinned-host tier, with headroom (reference tables hold <= 9) */
 #define QV_MAX_HOPS 8
 #define QV_IPC_HANDLE_BYTES 64 /* CUDA_IPC_HANDLE_SIZE */
@@ -77,11 +77,18 @@ QV_API int qv_free(int device, void *dev_ptr);
 QV_API int qv_upload_rows(int device, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
                    size_t rows);
 QV_API int qv_memset(int device, void *dst, int value, size_t bytes);
+/* Shard creation from DEVICE memory (extension; the reference's append() only takes CPU tensors, CHECK_CPU at
+ * quiver_feature.cu:19,147, so a table larger than host memory cannot be staged): device-to-device pitched row copy,
+ * asynchronous on `stream`.  A shard can also be created empty with qv_malloc and filled in place by the caller. */
+QV_API int qv_copy_rows_device(int device, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                        size_t rows, qv_stream_t stream);
 
 /* Zero-copy host tier: quiverRegister(cudaHostRegisterMapped) + cudaHostGetDevicePointer
  * (include/quiver/quiver.cu.hpp:16-26, quiver_feature.cu:192-199, quiver_sample.cu:413-421).
- * Registers [host_ptr, host_ptr+bytes) (page-rounded internally) and returns the device-visible alias.
- * Registering an already registered range is not an error. */
+ * Registers exactly [host_ptr, host_ptr+bytes) (cudaHostRegister accepts unaligned ranges and pins the pages they
+ * touch) and returns the device-visible alias.  Registering an already registered range is not an error: registrations
+ * are reference counted per base pointer, a longer range on the same base replaces the shorter one, and a range that
+ * someone else pinned (torch pin_memory) is used as is and never unregistered here. */
 QV_API int qv_host_register(int device, void *host_ptr, size_t bytes, void **dev_ptr);
 /* ShardTensor.unregister(cpu_tensor) -- quiver_feature.cu:354-360. */
 QV_API int qv_host_unregister(void *host_ptr);
@@ -141,6 +148,12 @@ QV_API int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes,
                       qv_sampler **out);
 QV_API int qv_sampler_destroy(qv_sampler *s);
 
+/* The `edge_ids` argument of device_quiver_from_csr_array (quiver_sample.cu:434-453: one id per CSR position, HBM copy
+ * or registered host alias; the reference stores it and every sampler then returns an empty e_id,
+ * sage_sampler.py:143).  Here it is used: the edge-id outputs below emit edge_ids[p] for a sampled CSR position p, or
+ * p itself while no array is set (NULL).  Borrowed, [n_edges] int64 valid on the sampler's device. */
+QV_API int qv_sampler_set_edge_ids(qv_sampler *s, const int64_t *edge_ids);
+
 /* Quiver.sample_neighbor, first half -- quiver_sample.cu:157-169 (degree, cap_by(k), exclusive_scan, reduce).
  *   counts[i] = min(deg(seeds[i]), k)   (k < 0: no cap; a seed outside [0, n_nodes) counts as degree 0)
  *   out_ptr   = exclusive_scan(counts);  *total = sum(counts)
@@ -152,9 +165,11 @@ QV_API int qv_sample_count(qv_sampler *s, const int64_t *seeds, int64_t S, int64
  * launched by quiver<T,CUDA>::new_sample (include/quiver/quiver.cu.hpp:380-403).  Writes, for every seed i, its
  * min(deg,k) sampled neighbour ids to neighbors[out_ptr[i] ...]: the row verbatim when deg <= k, otherwise
  * exactly the ids the reference kernel picks for generator seed `rand_seed` (the reference hard-codes 0).
- * Asynchronous. */
+ * edge_ids_out (optional, same layout as neighbors): the edge id of every sampled neighbour -- its CSR position
+ * indptr[seed] + pos, mapped through qv_sampler_set_edge_ids when set (the reference's sample kernel has
+ * the plumbing, quiver.cu.hpp:90-126, and drops the result).  Asynchronous. */
 QV_API int qv_sample_fill(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, uint64_t rand_seed,
-                   const int64_t *out_ptr, int64_t *neighbors, qv_stream_t stream);
+                   const int64_t *out_ptr, int64_t *neighbors, int64_t *edge_ids_out, qv_stream_t stream);
 
 /* Quiver.reindex_single(inputs, outputs, counts) -- quiver_sample.cu:305-357 (reindex_kernel :202-255,
  * FillWithDuplicates :18-63, DeviceOrderedHashTable include/quiver/reindex.cu.hpp:20-158).
@@ -173,12 +188,17 @@ QV_API int qv_reindex(qv_sampler *s, const int64_t *inputs, int64_t S, const int
  *   edge_buf[l] [2 * bound_edges[l]]      hop l's edge_index, stored as two back-to-back rows of out_edges[l]:
  *                                         [0,E) = source (neighbour) local ids, [E,2E) = target (seed) local ids,
  *                                         i.e. buf[:2E].view(2, E) is the contiguous PyG edge_index
+ *   eid_buf   NULL, or [n_hops] pointers (each NULL or [bound_edges[l]]): edge id of hop l's e-th edge (PyG's e_id;
+ *                                         see qv_sample_fill), valid prefix out_edges[l]
  *   out_nodes [n_hops+1], out_edges [n_hops]   host arrays: |frontier l| (out_nodes[0] = S) and E_l
- * All sizes[l] must be >= 0 (use the per-hop calls for "-1 = all neighbours"). */
+ * All sizes[l] must be >= 0 (use the per-hop calls for "-1 = all neighbours").
+ * With n_hops = 1 this is Quiver.sample_sub(stream_num, vertices, k) -- quiver_sample.cu:257-304 -- as ONE call:
+ * frontier = n_id, col_idx = edge_buf[0][0:E], row_idx = edge_buf[0][E:2E]. */
 QV_API int qv_khop_bounds(int64_t S, const int64_t *sizes, int n_hops, int64_t *bound_nodes /* [n_hops+1] */,
                    int64_t *bound_edges /* [n_hops] */);
 QV_API int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-            int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream);
+            int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, int64_t *out_nodes, int64_t *out_edges,
+            qv_stream_t stream);
 
 /* sample -> gather without returning to the host in between (the two reference calls it replaces are
  * GraphSageSampler.sample, sage_sampler.py:118-147, followed by Feature.__getitem__(n_id), feature.py:296-308).
@@ -186,12 +206,16 @@ QV_API int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
  * (qv_gather semantics; feature_order may be NULL).  The gather is enqueued BEHIND the sampling kernels with the
  * frontier size read on the device, and the host wait covers only the sampler's sizes: the call returns while the
  * gather may still be running on `stream` (stream-ordered like qv_gather).
- *   features  [bound_nodes[n_hops] * row_bytes]   caller-allocated to the static bound; valid prefix out_nodes[n_hops] rows
+ *   features  [features_rows * row_bytes]   caller-allocated; valid prefix out_nodes[n_hops] rows.  features_rows =
+ *             bound_nodes[n_hops] always suffices; a frontier holds distinct nodes, so min(bound, n_nodes + S) does too
+ *             (the adapter uses that: on graphs smaller than the fan-out bound it is many times smaller).  If the
+ *             frontier turns out larger than features_rows the first features_rows rows are gathered, the sample
+ *             outputs are complete and the call returns QV_ERR_UNSUPPORTED.
  * The table must be usable from the sampler's device. */
 QV_API int qv_khop_gather(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops,
-                   uint64_t rand_seed, int64_t *n_id, int64_t *const *edge_buf, const struct qv_shard_table *table,
-                   const int64_t *feature_order, int64_t row_bytes, void *features, int variant, int64_t *out_nodes,
-                   int64_t *out_edges, qv_stream_t stream);
+                   uint64_t rand_seed, int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf,
+                   const struct qv_shard_table *table, const int64_t *feature_order, int64_t row_bytes, void *features,
+                   int64_t features_rows, int variant, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream);
 
 /* Quiver.cal_neighbor_prob(stream_num, last_prob, cur_prob, k) -- quiver_sample.cu:100-111 launching cal_next
  * (include/quiver/cuda_random.cu.hpp:71-104): one hop of access-probability propagation, fp32, same operation

@@ -37,6 +37,8 @@ def _load():
     lib.qo_sample_counts.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp]
     lib.qo_sample_neighbor_gpu.restype = None
     lib.qo_sample_neighbor_gpu.argtypes = [u64, i64, i64, vp, vp, vp, vp, vp]
+    lib.qo_sample_neighbor_gpu_pos.restype = None
+    lib.qo_sample_neighbor_gpu_pos.argtypes = [u64, i64, i64, vp, vp, vp, vp, vp, vp]
     lib.qo_sample_neighbor_gpu_split.restype = None
     lib.qo_sample_neighbor_gpu_split.argtypes = [u64, i64, i64, vp, vp, vp, vp, vp, i64, i64]
     lib.qo_reindex.restype = i64
@@ -100,6 +102,18 @@ def sample_neighbor(indptr, indices, seeds, k, rand_seed=0):
     return out, counts
 
 
+def sample_neighbor_pos(indptr, indices, seeds, k, rand_seed=0):
+    """sample_neighbor plus the CSR position of every pick: (neighbors, counts, positions)."""
+    indptr, indices, seeds = _i64(indptr), _i64(indices), _i64(seeds)
+    if k < 0:
+        k = max(int(indptr.shape[0]) - 1, int(np.max(np.diff(indptr), initial=0)))
+    counts, out_ptr, tot = sample_counts(indptr, seeds, k)
+    out, pos = np.zeros(tot, np.int64), np.zeros(tot, np.int64)
+    _lib.qo_sample_neighbor_gpu_pos(int(rand_seed), int(k), seeds.shape[0], _p(seeds), _p(indptr), _p(indices),
+                                    _p(out_ptr), _p(out), _p(pos))
+    return out, counts, pos
+
+
 def sample_neighbor_split(indptr, indices, seeds, k, mega_draws, seg, rand_seed=0):
     """sample_neighbor with the chains of rows above `mega_draws` draws per lane cut into independent `seg`-draw segments
     positioned by offset skip-ahead (qo_sample_neighbor_gpu_split): must equal sample_neighbor exactly."""
@@ -120,14 +134,16 @@ def reindex(inputs, outputs, counts):
     return frontier[:F].copy(), row_idx, col_idx
 
 
-def khop(indptr, indices, seeds, sizes, rand_seed=0):
-    """GraphSageSampler.sample: (n_id, batch_size, [(edge_index[2,E], (n_src, n_dst))] outermost hop first)."""
+def khop(indptr, indices, seeds, sizes, rand_seed=0, with_eid=False):
+    """GraphSageSampler.sample: (n_id, batch_size, [(edge_index[2,E], (n_src, n_dst))] outermost hop first).
+    with_eid: every hop's tuple gains a third element, the CSR position of each sampled edge."""
     nodes = _i64(seeds)
     adjs = []
     for size in sizes:
-        out, cnt = sample_neighbor(indptr, indices, nodes, size, rand_seed)
+        out, cnt, pos = sample_neighbor_pos(indptr, indices, nodes, size, rand_seed)
         frontier, row_idx, col_idx = reindex(nodes, out, cnt)
-        adjs.append((np.stack([col_idx, row_idx]), (frontier.shape[0], nodes.shape[0])))
+        hop = (np.stack([col_idx, row_idx]), (frontier.shape[0], nodes.shape[0]))
+        adjs.append(hop + (pos, ) if with_eid else hop)
         nodes = frontier
     return nodes, len(seeds), adjs[::-1]
 
@@ -165,14 +181,40 @@ def validate_sample(indptr, indices, seeds, k, counts, out):
 
 
 # ---- the reference's own CPU extension (oracle/_ref, built by build_ref.py) -------------------------------------------
+_REF_NAMES = ("torch_quiver_ref", "torch_quiver_ref_omp", "torch_quiver_ref_cuda")
+
+
 def load_reference(openmp=False):
-    """Import the reference CPU extension compiled from /root/reference (None if it was never built)."""
+    """Import the reference CPU extension compiled from /root/reference (None if it was never built).
+
+    All builds of the reference register the same pybind11 types, so one process can hold only ONE of them: if one is
+    already imported it is returned (each carries the CPU classes; `cpu_quiver_from_csr_array` behaves the same)."""
+    for loaded in _REF_NAMES:
+        if loaded in sys.modules:
+            return sys.modules[loaded]
     name = "torch_quiver_ref_omp" if openmp else "torch_quiver_ref"
     if _REF_DIR not in sys.path:
         sys.path.insert(0, _REF_DIR)
     try:
         import torch  # noqa: F401  (the extension links libtorch)
         return importlib.import_module(name)
+    except ImportError:
+        return None
+
+
+def load_reference_cuda():
+    """Import the reference's CUDA extension recompiled for sm_100a by build_ref_cuda.py (None if absent or if another
+    build of the reference is already imported in this process).  Exposes the reference's `torch_quiver` surface:
+    device_quiver_from_csr_array / Quiver.sample_neighbor / reindex_single / ShardTensor / init_p2p, plus the CPU classes."""
+    if "torch_quiver_ref_cuda" in sys.modules:
+        return sys.modules["torch_quiver_ref_cuda"]
+    if any(n in sys.modules for n in _REF_NAMES):
+        return None
+    if _REF_DIR not in sys.path:
+        sys.path.insert(0, _REF_DIR)
+    try:
+        import torch  # noqa: F401
+        return importlib.import_module("torch_quiver_ref_cuda")
     except ImportError:
         return None
 

@@ -193,9 +193,9 @@ QO_API int64_t qo_sample_counts(const int64_t *indptr, int64_t n_nodes, int64_t 
  *   :61-64  out[j] = indices[row_start + slots[j]]
  *   :67     the lane's generator state persists over the warp's (up to 16) rows
  * ---------------------------------------------------------------------------------------------- */
-QO_API void qo_sample_neighbor_gpu(uint64_t rand_seed, int64_t k, int64_t S, const int64_t *seeds,
-                                   const int64_t *indptr, const int64_t *indices, const int64_t *out_ptr,
-                                   int64_t *out)
+static void sample_neighbor_gpu_impl(uint64_t rand_seed, int64_t k, int64_t S, const int64_t *seeds,
+                                     const int64_t *indptr, const int64_t *indices, const int64_t *out_ptr,
+                                     int64_t *out, int64_t *pos_out)
 {
     const int BLOCK_WARPS = 4, TILE = 64, WARP = 32;
     const int64_t grid = (S + TILE - 1) / TILE;
@@ -212,7 +212,10 @@ QO_API void qo_sample_neighbor_gpu(uint64_t rand_seed, int64_t k, int64_t S, con
                 const int64_t deg = indptr[row + 1] - start;
                 const int64_t o = out_ptr[out_row];
                 if (deg <= k) {
-                    for (int64_t j = 0; j < deg; j++) out[o + j] = indices[start + j];
+                    for (int64_t j = 0; j < deg; j++) {
+                        out[o + j] = indices[start + j];
+                        if (pos_out) pos_out[o + j] = start + j;
+                    }
                 } else {
                     for (int64_t j = 0; j < k; j++) slots[j] = j;
                     for (int l = 0; l < WARP; l++) {
@@ -222,12 +225,32 @@ QO_API void qo_sample_neighbor_gpu(uint64_t rand_seed, int64_t k, int64_t S, con
                             if ((int64_t)num < k && slots[num] < idx) slots[num] = idx;
                         }
                     }
-                    for (int64_t j = 0; j < k; j++) out[o + j] = indices[start + slots[j]];
+                    for (int64_t j = 0; j < k; j++) {
+                        out[o + j] = indices[start + slots[j]];
+                        if (pos_out) pos_out[o + j] = start + slots[j];
+                    }
                 }
             }
         }
     }
     free(slots);
+}
+
+QO_API void qo_sample_neighbor_gpu(uint64_t rand_seed, int64_t k, int64_t S, const int64_t *seeds,
+                                   const int64_t *indptr, const int64_t *indices, const int64_t *out_ptr,
+                                   int64_t *out)
+{
+    sample_neighbor_gpu_impl(rand_seed, k, S, seeds, indptr, indices, out_ptr, out, NULL);
+}
+
+/* Same walk, also reporting WHERE each pick sits in the CSR: pos_out[e] = indptr[seed] + slot -- the position whose
+ * edge id the reference's sample kernel would emit (quiver.cu.hpp:90-126 `begin_id`), had any caller kept it
+ * (sage_sampler.py:143 returns an empty e_id).  Checks the product's opt-in e_id output. */
+QO_API void qo_sample_neighbor_gpu_pos(uint64_t rand_seed, int64_t k, int64_t S, const int64_t *seeds,
+                                       const int64_t *indptr, const int64_t *indices, const int64_t *out_ptr,
+                                       int64_t *out, int64_t *pos_out)
+{
+    sample_neighbor_gpu_impl(rand_seed, k, S, seeds, indptr, indices, out_ptr, out, pos_out);
 }
 
 /* ------------------------------------------------------------------------------------------------

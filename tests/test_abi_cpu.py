@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert declared <= exported, f"declared but not exported: {sorted(declared - exported)}"
     assert exported <= declared, f"exported but not declared: {sorted(exported - declared)}"
     assert set(_lib.PROTOTYPES) == declared  # the Python adapter binds exactly the header's surface
-    assert _lib.lib.qv_abi_version() == 1
+    assert _lib.lib.qv_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

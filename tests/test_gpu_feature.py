@@ -315,3 +315,32 @@ def test_from_mmap_with_id_parts_and_saved_parts(tmp_path):
     g.from_mmap(None, DeviceConfig([str(tmp_path / "gpu0.pth")], str(tmp_path / "cpu.pth")))
     g.set_local_order(perm)
     assert torch.equal(g[idx.cuda()].cpu(), want)
+
+
+def test_shards_created_from_device_memory(oracle):
+    """Extension for tables larger than host memory (C5 / north-star): a shard copied from a CUDA tensor (the reference
+    refuses: CHECK_CPU, quiver_feature.cu:19,147) and a shard created empty in HBM and filled in place."""
+    import torch_quiver as qv
+    n, d = 50000, 100  # 400-byte rows: the shard pitch stays 400; d = 602 below pads 2408 -> 2416
+    for d in (100, 602, 256):
+        x = torch.from_numpy(np.random.default_rng(d).integers(0, 10, (n, d)).astype(np.float32))
+        idx = torch.from_numpy(np.random.default_rng(1).integers(0, n, 70000)).cuda()
+        st = qv.ShardTensor(0)
+        st.append(x[:20000].cuda(), 0)                                   # device -> shard copy (pitched)
+        view = st.append_empty(n - 20000 - 5000, [d], torch.float32, 0)  # in place: the caller writes the rows
+        assert view.shape == (n - 25000, d) and view.is_cuda and view.stride(0) * 4 == st.shards[-1].pitch
+        view.copy_(x[20000:n - 5000].cuda())
+        st.append(x[n - 5000:].clone(), -1)                              # plus a pinned-host tier behind them
+        assert st.shape() == [n, d] and st.device_count() == 3
+        got = st[idx]
+        assert torch.equal(got.cpu(), x[idx.cpu()])
+        want = oracle.gather([x.numpy()], idx.cpu().numpy())
+        assert np.array_equal(got.cpu().numpy(), want)
+        items = st.share_ipc()  # both HBM shards are the library's own allocations: exportable
+        assert len(items) == 2 and items[1].shape == [n - 25000, d]
+    fp16 = qv.ShardTensor(0)
+    v = fp16.append_empty(1000, [64], torch.float16, 0)
+    ref = torch.randn(1000, 64).half()
+    v.copy_(ref.cuda())
+    sel = torch.arange(999, -1, -1).cuda()
+    assert torch.equal(fp16[sel].cpu(), ref[sel.cpu()])

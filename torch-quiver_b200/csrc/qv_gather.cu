@@ -559,15 +559,18 @@ int gather_enqueue(const qv_shard_table *table, const int64_t *indices, const in
     // peak, with no payload in registers); shorter rows are faster with 16-byte SIMT accesses (0.80 vs 0.67 at 400 B)
     if (variant == 2 || (variant == 0 && chunk == 16 && row_bytes >= 2048 && row_bytes <= 8 * 1024)) {
         QV_REQUIRE(chunk == 16, "qv_gather: the TMA variant needs 16-byte aligned rows, pitches and pointers");
-        QV_REQUIRE(row_bytes <= 48 * 1024, "qv_gather: the TMA variant supports rows up to 48 KiB");
+        QV_REQUIRE(row_bytes <= 32 * 1024, "qv_gather: the TMA variant supports rows up to 32 KiB");
         // stage = up to 32 rows of ~8 KiB in total; 6 stages per CTA, several CTAs per SM
         int rows_per_stage = static_cast<int>(std::min<int64_t>(32, (8 * 1024) / row_bytes));
         rows_per_stage = std::max(rows_per_stage, 1);
         const size_t smem = static_cast<size_t>(kTmaStages) * rows_per_stage * row_bytes;
-        static bool attr_set[64] = {false};
-        if (device < 0 || device >= 64 || !attr_set[device]) {
+        QV_REQUIRE(smem <= 200 * 1024, "qv_gather: the TMA variant stages %d rows x %d buffers: rows above %d bytes do not fit",
+                   rows_per_stage, kTmaStages, 200 * 1024 / kTmaStages);
+        static std::atomic<unsigned long long> attr_set{0};  // bit d: the attribute is set on device d (any thread may race here: setting it twice is harmless)
+        const unsigned long long bit = (device >= 0 && device < 64) ? 1ull << device : 0ull;
+        if (!(attr_set.load(std::memory_order_acquire) & bit) || bit == 0) {
             QV_CUDA(cudaFuncSetAttribute(gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            if (device >= 0 && device < 64) attr_set[device] = true;
+            attr_set.fetch_or(bit, std::memory_order_release);
         }
         const int64_t n_groups = (n + rows_per_stage - 1) / rows_per_stage;
         const int ctas_per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(16, (200 * 1024) / (smem + 1024))));

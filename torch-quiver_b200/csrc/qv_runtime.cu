@@ -52,6 +52,7 @@ std::mutex g_reg_mu;
 struct Registration {
     size_t bytes;
     int refs;
+    bool ours;  // false: the range was already pinned by someone else (torch pin_memory, ...) -- never unregistered here
 };
 std::unordered_map<void *, Registration> g_registered;
 }  // namespace
@@ -155,6 +156,22 @@ int qv_upload_rows(int device, void *dst, size_t dst_pitch, const void *src, siz
     return QV_OK;
 }
 
+int qv_copy_rows_device(int device, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                        size_t rows, qv_stream_t stream)
+{
+    if (rows == 0 || row_bytes == 0) return QV_OK;
+    QV_REQUIRE(dst && src, "qv_copy_rows_device: NULL pointer");
+    QV_REQUIRE(dst_pitch >= row_bytes && src_pitch >= row_bytes, "qv_copy_rows_device: pitch smaller than row");
+    DeviceGuard g(device);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dst_pitch == row_bytes && src_pitch == row_bytes) {
+        QV_CUDA(cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyDeviceToDevice, st));
+    } else {
+        QV_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToDevice, st));
+    }
+    return QV_OK;
+}
+
 int qv_memset(int device, void *dst, int value, size_t bytes)
 {
     if (!bytes) return QV_OK;
@@ -174,16 +191,30 @@ int qv_host_register(int device, void *host_ptr, size_t bytes, void **dev_ptr)
     if (it != g_registered.end() && it->second.bytes >= bytes) {
         it->second.refs++;  // same tensor shared by several tables: one registration, counted
     } else {
+        if (it != g_registered.end() && it->second.ours) {
+            // same base, LONGER range than the one we hold: the old mapping does not cover it -- replace it under the
+            // lock (the users of the shorter range keep a valid alias: a registration of [p, p+n) yields the same device
+            // address for p whatever n is) and carry their references over
+            cudaError_t e = cudaHostUnregister(host_ptr);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(QV_ERR_CUDA, "cudaHostUnregister(%p) before re-registering %zu bytes: %s", host_ptr, bytes,
+                            cudaGetErrorString(e));
+            }
+        }
+        const int carried = it != g_registered.end() ? it->second.refs : 0;
         // One registration for the whole range: the reference splits it into 1e9-byte pieces whose boundaries are
         // not page aligned (quiver.cu.hpp:19-25); a single cudaHostRegister has no such seams.
         cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
         if (e == cudaErrorHostMemoryAlreadyRegistered) {
-            cudaGetLastError();  // pinned by someone else (e.g. torch pin_memory): usable, not ours to undo
+            cudaGetLastError();  // pinned by someone else (e.g. torch pin_memory): usable, not ours to undo -- recorded
+            g_registered[host_ptr] = Registration{bytes, carried + 1, false};  // as foreign so that it is never unregistered here
         } else if (e != cudaSuccess) {
             cudaGetLastError();
+            if (it != g_registered.end()) g_registered.erase(host_ptr);
             return fail(QV_ERR_CUDA, "cudaHostRegister(%p, %zu): %s", host_ptr, bytes, cudaGetErrorString(e));
         } else {
-            g_registered[host_ptr] = Registration{bytes, 1};
+            g_registered[host_ptr] = Registration{bytes, carried + 1, true};
         }
     }
     QV_CUDA(cudaHostGetDevicePointer(dev_ptr, host_ptr, 0));
@@ -197,8 +228,9 @@ int qv_host_unregister(void *host_ptr)
     auto it = g_registered.find(host_ptr);
     if (it == g_registered.end()) return QV_OK;  // not ours (or already undone)
     if (--it->second.refs > 0) return QV_OK;
+    const bool ours = it->second.ours;
     g_registered.erase(it);
-    QV_CUDA(cudaHostUnregister(host_ptr));
+    if (ours) QV_CUDA(cudaHostUnregister(host_ptr));
     return QV_OK;
 }
 

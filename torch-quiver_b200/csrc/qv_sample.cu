@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
                              const int64_t *__restrict__ cached_deg, MapWord *__restrict__ node_map, unsigned int epoch_hi,
                              int64_t item_base_arg, const int64_t *__restrict__ d_item_base,
                              int64_t *__restrict__ d_err, unsigned long long *__restrict__ heavy, int late_wait,
-                             const uint32_t *__restrict__ jump_mats)
+                             const uint32_t *__restrict__ jump_mats, int64_t *__restrict__ eid_out,
+                             const int64_t *__restrict__ edge_ids)
 {
     // dynamic shared memory, sized by the fan-out: per warp 16*k staged ids (8 B), 16*k reservoir slots (4 B) and 16*k
     // entry->row bytes -- 4 KiB per block at k = 5 instead of a fixed 26 KiB, which lifts the occupancy limit
@@ -794,6 +795,17 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks)
         const int64_t id = stage_w[e];
         out[dst] = id;
         if (row_out) row_out[row_off + dst] = b * kSampleTile + w + static_cast<int64_t>(i) * kSampleWarps;
+        if (eid_out) {  // edge id = CSR position of the pick (the reservoirs are final: recompute it instead of carrying it)
+            const uint32_t j = e - pre_sh[wp][i];
+            uint32_t pos = j;
+            if (deg_sh[wp][i] > kk) {
+                pos = slots_w[static_cast<size_t>(i) * kcap + j];
+                if (mega_mask && (mega_mask >> i & 1u))
+                    pos = max(__ldcv(reinterpret_cast<const unsigned int *>(heavy + kAuxMegaSlots) + mega_sh[wp][i] * 32 + j), j);
+            }
+            const int64_t p = start_sh[wp][i] + pos;
+            eid_out[dst] = edge_ids ? edge_ids[p] : p;
+        }
         if (node_map) {  // fused k-hop: the sampled id enters the first-occurrence map right here
             if (static_cast<uint64_t>(id) < static_cast<uint64_t>(n_nodes))
                 atomicMin(&node_map[id], map_word(epoch_hi, kMapCand + static_cast<unsigned int>(item_base + dst)));
@@ -850,7 +862,8 @@ __global__ void __launch_bounds__(256)
                             const int64_t *__restrict__ out_ptr, const int64_t *__restrict__ d_E, uint32_t key0,
                             uint32_t key1, int64_t *__restrict__ out, int64_t *__restrict__ row_out,
                             const int64_t *__restrict__ d_row_off, const int64_t *__restrict__ cached_start,
-                            const int64_t *__restrict__ cached_deg)
+                            const int64_t *__restrict__ cached_deg, int64_t *__restrict__ eid_out,
+                            const int64_t *__restrict__ edge_ids)
 {
     pdl_wait();
     const int64_t S = dev_size(S_arg, d_S);
@@ -885,6 +898,7 @@ __global__ void __launch_bounds__(256)
                                                                          key1 ^ static_cast<uint32_t>(node >> 32)));
         out[e] = indices[start + pos];
         if (row_out) row_out[row_off + e] = r;
+        if (eid_out) eid_out[e] = edge_ids ? edge_ids[start + pos] : start + pos;
     }
 }
 
@@ -893,7 +907,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
     sample_rows_kernel(const int64_t *__restrict__ indptr, const int64_t *__restrict__ indices, int64_t n_nodes,
                        const int64_t *__restrict__ seeds, int64_t S_arg, const int64_t *__restrict__ d_S, int64_t k_arg,
                        const int64_t *__restrict__ out_ptr, const uint32_t *__restrict__ rng_states, const RecipTable rt,
-                       int64_t *__restrict__ out, int64_t *__restrict__ row_out, const int64_t *__restrict__ d_row_off)
+                       int64_t *__restrict__ out, int64_t *__restrict__ row_out, const int64_t *__restrict__ d_row_off,
+                       int64_t *__restrict__ eid_out, const int64_t *__restrict__ edge_ids)
 {
     __shared__ uint32_t slots_sh[kSlotsInSmem ? kSampleWarps * kSmemSlots : 1];
     const int64_t S = dev_size(S_arg, d_S);
@@ -939,7 +954,10 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
         if (row_out)
             for (int64_t j = lane; j < cnt; j += 32) row_out[row_off + o + j] = r;
         if (deg <= k) {
-            for (int64_t j = lane; j < deg; j += 32) out[o + j] = indices[start + j];
+            for (int64_t j = lane; j < deg; j += 32) {
+                out[o + j] = indices[start + j];
+                if (eid_out) eid_out[o + j] = edge_ids ? edge_ids[start + j] : start + j;
+            }
         } else if (kSlotsInSmem) {
             const uint32_t kk = static_cast<uint32_t>(k);
             for (uint32_t j = lane; j < kk; j += 32) slots[j] = j;
@@ -947,7 +965,11 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             const uint32_t udeg = static_cast<uint32_t>(deg);
             reservoir_fill<kFast>(rng, rt, kk, udeg, lane, slots);
             __syncwarp();
-            for (uint32_t j = lane; j < kk; j += 32) out[o + j] = indices[start + slots[j]];
+            for (uint32_t j = lane; j < kk; j += 32) {
+                const int64_t p = start + slots[j];
+                out[o + j] = indices[p];
+                if (eid_out) eid_out[o + j] = edge_ids ? edge_ids[p] : p;
+            }
             __syncwarp();
         } else {
             unsigned long long *gs = reinterpret_cast<unsigned long long *>(out + o);
@@ -961,6 +983,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32)
             for (int64_t j = lane; j < k; j += 32) {
                 const int64_t pos = static_cast<int64_t>(gs[j]);
                 out[o + j] = indices[start + pos];
+                if (eid_out) eid_out[o + j] = edge_ids ? edge_ids[start + pos] : start + pos;
             }
             __syncwarp();
         }
@@ -1383,6 +1406,7 @@ struct qv_sampler {
     Buffer recip;    // fastmod reciprocals for divisors [0, recip_n)
     unsigned int recip_n = 0;
     int64_t max_degree = 0;
+    const int64_t *edge_ids = nullptr;  // optional user edge ids per CSR position (qv_sampler_set_edge_ids); borrowed
 };
 
 namespace
@@ -1477,6 +1501,7 @@ struct HopExtras {  // fused k-hop only; all null for the standalone calls
     unsigned long long *heavy = nullptr;  // longest-first list (kHeavyWords, zeroed): filled by count_scan, read by the sampler
     int late_wait = 0;                    // the sampling kernel waits for count_scan only before its write-out
     const uint32_t *jump_mats = nullptr;  // XORWOW jump matrices: non-null enables chain splitting of mega rows
+    int64_t *eid_out = nullptr;           // optional edge-id output of the hop (any caller, not only the fused k-hop)
 };
 
 int launch_count_scan(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int64_t *d_S, int64_t S_bound,
@@ -1506,7 +1531,8 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
         const uint64_t h = (rand_seed ^ (c * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
         QV_CUDA(launch_chained(sample_rows_fast_kernel, grid_for(E_bound, 256, s->n_sm), 256, 0, st, s->indptr, s->indices,
                                s->n_nodes, seeds, S_arg, d_S, k, out_ptr, d_E, static_cast<uint32_t>(h),
-                               static_cast<uint32_t>(h >> 32), out, row_out, d_row_off, x.cached_start, x.cached_deg));
+                               static_cast<uint32_t>(h >> 32), out, row_out, d_row_off, x.cached_start, x.cached_deg,
+                               x.eid_out, s->edge_ids));
         QV_CHECK_LAUNCH("sample_rows_fast_kernel");
         return QV_OK;
     }
@@ -1528,24 +1554,27 @@ int launch_sample(qv_sampler *s, const int64_t *seeds, int64_t S_arg, const int6
                                    small_smem, st, s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S,
                                    static_cast<int>(k), out_ptr, states, rt, out, row_out, d_row_off, x.cached_start,
                                    x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err, x.heavy,
-                                   x.late_wait, x.jump_mats));
+                                   x.late_wait, x.jump_mats, x.eid_out, s->edge_ids));
         else
             sample_rows_small_kernel<false, 4, 8><<<static_cast<unsigned>(blocks + (x.heavy ? kHeavyBlocks : 0) +
                                                                           (x.jump_mats ? kMegaBlocks : 0)),
                                                     kSampleWarps * 32, small_smem, st>>>(
                 s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, static_cast<int>(k), out_ptr, states, rt, out,
                 row_out, d_row_off, x.cached_start, x.cached_deg, x.node_map, x.epoch_hi, x.item_base, x.d_item_base, x.d_err,
-                x.heavy, 0, x.jump_mats);
+                x.heavy, 0, x.jump_mats, x.eid_out, s->edge_ids);
         if (fused_insert) *fused_insert = x.node_map != nullptr && x.d_err != nullptr;
     } else if (impl & 2) {
         sample_rows_kernel<true, false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off, x.eid_out,
+            s->edge_ids);
     } else if (k < 0 || k <= kSmemSlots) {
         sample_rows_kernel<true><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off, x.eid_out,
+            s->edge_ids);
     } else {
         sample_rows_kernel<false><<<static_cast<unsigned>(blocks), kSampleWarps * 32, 0, st>>>(
-            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off);
+            s->indptr, s->indices, s->n_nodes, seeds, S_arg, d_S, k, out_ptr, states, rt, out, row_out, d_row_off, x.eid_out,
+            s->edge_ids);
     }
     QV_CHECK_LAUNCH("sample_rows_kernel");
     return QV_OK;
@@ -1693,8 +1722,15 @@ int qv_sample_count(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, i
     return QV_OK;
 }
 
+int qv_sampler_set_edge_ids(qv_sampler *s, const int64_t *edge_ids)
+{
+    QV_REQUIRE(s != nullptr, "qv_sampler_set_edge_ids: NULL sampler");
+    s->edge_ids = edge_ids;
+    return QV_OK;
+}
+
 int qv_sample_fill(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, uint64_t rand_seed,
-                   const int64_t *out_ptr, int64_t *neighbors, qv_stream_t stream)
+                   const int64_t *out_ptr, int64_t *neighbors, int64_t *edge_ids_out, qv_stream_t stream)
 {
     QV_REQUIRE(s, "qv_sample_fill: NULL sampler");
     if (S <= 0) return QV_OK;
@@ -1702,8 +1738,10 @@ int qv_sample_fill(qv_sampler *s, const int64_t *seeds, int64_t S, int64_t k, ui
     QV_REQUIRE(k < (int64_t(1) << 31), "qv_sample_fill: fan-out %lld too large", (long long)k);
     DeviceGuard g(s->device);
     // fast mode needs the total (left in d_meta by the qv_sample_count call that sized `neighbors`)
+    HopExtras x;
+    x.eid_out = edge_ids_out;
     return launch_sample(s, seeds, S, nullptr, S, k, rand_seed, out_ptr, neighbors, nullptr, nullptr,
-                         static_cast<cudaStream_t>(stream), HopExtras(), nullptr, s->d_meta + kMetaE,
+                         static_cast<cudaStream_t>(stream), x, nullptr, s->d_meta + kMetaE,
                          s->fast ? s->h_meta[kMetaE] : 0);
 }
 
@@ -1767,13 +1805,14 @@ struct GatherTail {
     const int64_t *feature_order = nullptr;
     int64_t row_bytes = 0;
     void *features = nullptr;
+    int64_t capacity_rows = 0;  // rows `features` can hold (<= the static frontier bound)
     int variant = 0;
 };
 
 // One attempt of the fused k-hop.  use_map: direct node map (default) or the per-hop hash table.
 int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-             int64_t *n_id, int64_t *const *edge_buf, const int64_t *bn, const int64_t *be, bool use_map, cudaStream_t st,
-             bool *id_error, const GatherTail &tail)
+             int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, const int64_t *bn, const int64_t *be,
+             bool use_map, cudaStream_t st, bool *id_error, const GatherTail &tail)
 {
     int64_t *optr = static_cast<int64_t *>(s->out_ptr.ptr);
     int64_t *nbr_base = static_cast<int64_t *>(s->nbr.ptr);
@@ -1824,6 +1863,7 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         emit.col[h] = edge_buf[h];
         emit.begin[h + 1] = emit.begin[h] + be[h];
         HopExtras x;
+        x.eid_out = eid_buf ? eid_buf[h] : nullptr;
         int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start ? fr_start + bn[n_hops] : nullptr;
         if (use_map) {
             x.node_map = map;
@@ -1915,8 +1955,8 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
         // while the rows are being copied.  After an id error n_id holds arbitrary values: the gather range-checks every
         // id (zero rows), and the whole call is redone by the caller.
         const int64_t *d_n = s->d_meta + kMetaStride * (n_hops - 1) + kMetaF;
-        QV_TRY(gather_enqueue(tail.table, n_id, tail.feature_order, bn[n_hops], d_n, tail.row_bytes, tail.features,
-                              tail.variant, st));
+        QV_TRY(gather_enqueue(tail.table, n_id, tail.feature_order, std::min(bn[n_hops], tail.capacity_rows), d_n,
+                              tail.row_bytes, tail.features, tail.variant, st));
     }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
     if (use_map && s->h_meta[kMetaErr] != 0) {
@@ -1927,20 +1967,22 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
 }
 
 int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-               int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream,
-               const GatherTail &tail);
+               int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, int64_t *out_nodes, int64_t *out_edges,
+               qv_stream_t stream, const GatherTail &tail);
 }  // namespace
 
 int qv_khop(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-            int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream)
+            int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, int64_t *out_nodes, int64_t *out_edges,
+            qv_stream_t stream)
 {
-    return khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, out_nodes, out_edges, stream, GatherTail());
+    return khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, out_nodes, out_edges, stream,
+                      GatherTail());
 }
 
 int qv_khop_gather(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-                   int64_t *n_id, int64_t *const *edge_buf, const qv_shard_table *table, const int64_t *feature_order,
-                   int64_t row_bytes, void *features, int variant, int64_t *out_nodes, int64_t *out_edges,
-                   qv_stream_t stream)
+                   int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, const qv_shard_table *table,
+                   const int64_t *feature_order, int64_t row_bytes, void *features, int64_t features_rows, int variant,
+                   int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream)
 {
     QV_REQUIRE(table != nullptr, "qv_khop_gather: table is NULL");
     QV_REQUIRE(features != nullptr || S == 0, "qv_khop_gather: features is NULL");
@@ -1950,15 +1992,22 @@ int qv_khop_gather(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
     tail.feature_order = feature_order;
     tail.row_bytes = row_bytes;
     tail.features = features;
+    tail.capacity_rows = features_rows;
     tail.variant = variant;
-    return khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, out_nodes, out_edges, stream, tail);
+    QV_REQUIRE(features_rows >= 0, "qv_khop_gather: features_rows = %lld", (long long)features_rows);
+    QV_TRY(khop_entry(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, out_nodes, out_edges, stream, tail));
+    if (out_nodes[n_hops] > features_rows)
+        return fail(QV_ERR_UNSUPPORTED, "qv_khop_gather: the frontier has %lld rows, `features` holds %lld: only those were "
+                    "gathered (sample results are complete; gather the rest with qv_gather)", (long long)out_nodes[n_hops],
+                    (long long)features_rows);
+    return QV_OK;
 }
 
 namespace
 {
 int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
-               int64_t *n_id, int64_t *const *edge_buf, int64_t *out_nodes, int64_t *out_edges, qv_stream_t stream,
-               const GatherTail &tail)
+               int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, int64_t *out_nodes, int64_t *out_edges,
+               qv_stream_t stream, const GatherTail &tail)
 {
     QV_REQUIRE(s && sizes && out_nodes && out_edges, "qv_khop: NULL argument");
     int64_t bn[QV_MAX_HOPS + 1], be[QV_MAX_HOPS];
@@ -1996,10 +2045,10 @@ int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *si
         s->fr_meta.release();
 
     bool id_error = false;
-    QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, use_map, st, &id_error, tail));
+    QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, bn, be, use_map, st, &id_error, tail));
     if (id_error) {
         QV_TRY(ensure_table(s, bn[n_hops]));
-        QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, bn, be, false, st, &id_error, tail));
+        QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, bn, be, false, st, &id_error, tail));
     }
     for (int h = 0; h < n_hops; h++) {
         out_edges[h] = s->h_meta[kMetaStride * h + kMetaE];

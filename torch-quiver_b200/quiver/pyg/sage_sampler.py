@@ -59,9 +59,13 @@ class GraphSageSampler:
         device (int): GPU the kernels run on
         mode (str): "GPU" (topology in HBM) or "UVA" (indices stay in pinned host memory, read zero-copy).
             "CPU" is accepted by the reference; this build has no CPU path and raises for it.
+        return_eid (bool): extension.  False (default) = the reference's behaviour: every `Adj.e_id` is
+            an empty tensor (sage_sampler.py:143).  True: `Adj.e_id[e]` is the id of edge e of that hop -- its position
+            in `csr_topo.indices`, or `csr_topo.eid[position]` when the topology carries edge ids -- as PyG's
+            NeighborSampler returns it.
     """
 
-    def __init__(self, csr_topo: quiver_utils.CSRTopo, sizes: List[int], device=0, mode="UVA"):
+    def __init__(self, csr_topo: quiver_utils.CSRTopo, sizes: List[int], device=0, mode="UVA", return_eid=False):
         assert mode in ["UVA", "GPU", "CPU"], "sampler mode should be one of [UVA, GPU]"
         assert device is _FakeDevice or mode == "CPU" or (device >= 0 and mode != "CPU"), \
             "Device setting and Mode setting not compatitive"
@@ -73,6 +77,7 @@ class GraphSageSampler:
         self.csr_topo = csr_topo
         self.mode = mode
         self.fused = True  # all hops in one C call; falls back per hop when a size is -1
+        self.return_eid = bool(return_eid)
         # The fused sampler runs on its own high-priority CUDA stream (the reference also samples on a private stream
         # pool, quiver_sample.cu:116-117), so a sample() call overlaps whatever the caller left running on the current
         # stream -- typically the previous batch's feature gather or training step.  The call still returns only when
@@ -89,7 +94,7 @@ class GraphSageSampler:
         self.ipc_handle_ = None
 
     def _build(self, device):
-        edge_id = torch.zeros(1, dtype=torch.long)
+        edge_id = self.csr_topo.eid if self.csr_topo.eid is not None else torch.zeros(1, dtype=torch.long)
         return qv.device_quiver_from_csr_array(self.csr_topo.indptr, self.csr_topo.indices, edge_id, device,
                                                self.mode != "UVA")
 
@@ -123,24 +128,35 @@ class GraphSageSampler:
                 if self.overlap:
                     n_id, hops = self._sample_khop_overlapped(input_nodes)
                 else:
-                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes)
+                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes,
+                                                         with_eid=self.return_eid)
             except qv.Unsupported:
                 pass
             else:
                 # e_id is always empty in the reference (sage_sampler.py:143); one shared empty tensor, one host tensor
                 # for all the (n_src, n_dst) pairs
-                sizes = torch.tensor([[n_src, n_dst] for _, n_src, n_dst in hops], dtype=torch.long)
-                adjs = [Adj(hop[0], _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
-                return n_id, batch_size, adjs[::-1]
+                return n_id, batch_size, self._adjs(hops)
         nodes = input_nodes.to(self.device)
         adjs = []
         for size in self.sizes:
-            out, cnt = self.sample_layer(nodes, size)
+            if self.return_eid:
+                k = size if size != -1 else self.csr_topo.node_count
+                out, cnt, e_id = self.quiver.sample_neighbor(0, nodes, k, return_eid=True)
+            else:
+                (out, cnt), e_id = self.sample_layer(nodes, size), torch.tensor([])
             frontier, row_idx, col_idx = self.reindex(nodes, out, cnt)
             edge_index = torch.stack([col_idx, row_idx], dim=0)  # [source local id, target (seed) position]
-            adjs.append(Adj(edge_index, torch.tensor([]), torch.LongTensor([frontier.size(0), nodes.size(0)])))
+            adjs.append(Adj(edge_index, e_id, torch.LongTensor([frontier.size(0), nodes.size(0)])))
             nodes = frontier
         return nodes, batch_size, adjs[::-1]
+
+    @staticmethod
+    def _adjs(hops):
+        """hops (innermost first) of Quiver.sample_khop -> the PyG Adj list, outermost hop first.  e_id is one shared empty
+        tensor unless the hop tuples carry edge ids (return_eid); the (n_src, n_dst) pairs share one host tensor."""
+        sizes = torch.tensor([[hop[1], hop[2]] for hop in hops], dtype=torch.long)
+        adjs = [Adj(hop[0], hop[3] if len(hop) > 3 else _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
+        return adjs[::-1]
 
     def sample_and_gather(self, input_nodes, feature):
         """Extension: `n_id, bs, adjs = sample(seeds); x = feature[n_id]` as ONE device pipeline.
@@ -159,13 +175,11 @@ class GraphSageSampler:
                 and torch.cuda.current_device() == self.device):
             try:
                 n_id, hops, x = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes,
-                                                        gather=(store, order))
+                                                        gather=(store, order), with_eid=self.return_eid)
             except qv.Unsupported:
                 pass
             else:
-                sizes = torch.tensor([[n_src, n_dst] for _, n_src, n_dst in hops], dtype=torch.long)
-                adjs = [Adj(hop[0], _EMPTY_E_ID, sizes[i]) for i, hop in enumerate(hops)]
-                return n_id, batch_size, adjs[::-1], x
+                return n_id, batch_size, self._adjs(hops), x
         n_id, batch_size, adjs = self.sample(input_nodes)
         return n_id, batch_size, adjs, feature[n_id]
 
@@ -177,7 +191,7 @@ class GraphSageSampler:
             priv.wait_stream(cur)  # the seeds may still be in flight on the caller's stream
         with torch.cuda.stream(priv):
             nodes = input_nodes.to(self.device)
-            n_id, hops = self.quiver.sample_khop(nodes, self.sizes)  # returns after synchronising `priv`
+            n_id, hops = self.quiver.sample_khop(nodes, self.sizes, with_eid=self.return_eid)  # returns after synchronising `priv`
         n_id.record_stream(cur)  # one arena backs n_id and every edge_index: keep it alive for the consumer stream
         return n_id, hops
 

@@ -74,7 +74,7 @@ def init_p2p(devices):
 class Quiver:
     """Device CSR + sampler scratch.  Mirrors `torch_quiver.Quiver` (class TorchQuiver, quiver_sample.cu:77-357)."""
 
-    def __init__(self, indptr, indices, device, cuda):
+    def __init__(self, indptr, indices, device, cuda, edge_ids=None):
         self.device = int(device)
         self.rand_seed = 0  # the reference hard-codes 0 (quiver.cu.hpp:392); change it to draw a different sample
         self._keep = []  # tensors whose memory the C object borrows
@@ -108,15 +108,34 @@ class Quiver:
         self.edge_count = indices.numel()
         check(lib.qv_sampler_create(self.device, _ptr(indptr_d), self.node_count, c_void_p(indices_ptr),
                                     self.edge_count, byref(self._handle)))
-        self._finalizer = weakref.finalize(self, Quiver._destroy, self._handle.value,
-                                           self._registered.data_ptr() if self._registered is not None else None)
+        registered = [self._registered.data_ptr()] if self._registered is not None else []
+        # edge ids: used iff there is one per edge (quiver_sample.cu:385-387 `use_eid`); HBM copy or zero-copy alias, like
+        # `indices` (quiver_sample.cu:434-453).  They feed the opt-in e_id outputs; without them e_id = CSR position.
+        self.has_edge_ids = False
+        if edge_ids is not None and edge_ids.dim() == 1 and edge_ids.numel() == self.edge_count and self.edge_count > 0:
+            if edge_ids.dtype != torch.int64:
+                raise RuntimeError("edge_ids must be torch.long")
+            if cuda or edge_ids.is_cuda:
+                eid_d = edge_ids.to(dev).contiguous()
+                self._keep.append(eid_d)
+                eid_ptr = eid_d.data_ptr()
+            else:
+                eid_c = edge_ids.contiguous()
+                self._keep.append(eid_c)
+                alias = c_void_p()
+                check(lib.qv_host_register(self.device, _ptr(eid_c), eid_c.numel() * 8, byref(alias)))
+                registered.append(eid_c.data_ptr())
+                eid_ptr = alias.value
+            check(lib.qv_sampler_set_edge_ids(self._handle, c_void_p(eid_ptr)))
+            self.has_edge_ids = True
+        self._finalizer = weakref.finalize(self, Quiver._destroy, self._handle.value, tuple(registered))
 
     @staticmethod
-    def _destroy(handle, registered_ptr):
+    def _destroy(handle, registered_ptrs):
         if handle:
             lib.qv_sampler_destroy(c_void_p(handle))
-        if registered_ptr:
-            lib.qv_host_unregister(c_void_p(registered_ptr))
+        for ptr in registered_ptrs:
+            lib.qv_host_unregister(c_void_p(ptr))
 
     def set_fast(self, enabled=True):
         """Extension: O(k)-per-row sampling that is NOT the reference's random stream (see qv_sampler_set_fast)."""
@@ -124,7 +143,9 @@ class Quiver:
         self.fast = bool(enabled)
 
     # -- Quiver.sample_neighbor(stream_num, vertices, k) ------------------------------------------------------------
-    def sample_neighbor(self, stream_num, vertices, k):
+    def sample_neighbor(self, stream_num, vertices, k, return_eid=False):
+        """(neighbors, counts); with return_eid=True (extension) also the edge id of every sampled
+        neighbour: its CSR position, or edge_ids[position] when the object was built with edge ids."""
         v = _check_long_cuda(vertices, "vertices", self.device)
         S = v.numel()
         counts = torch.empty(S, dtype=torch.int64, device=v.device)
@@ -133,8 +154,11 @@ class Quiver:
         st = _stream(self.device)
         check(lib.qv_sample_count(self._handle, _ptr(v), S, int(k), _ptr(counts), _ptr(out_ptr), byref(total), st))
         neighbors = torch.empty(total.value, dtype=torch.int64, device=v.device)
+        eid = torch.empty(total.value, dtype=torch.int64, device=v.device) if return_eid else None
         check(lib.qv_sample_fill(self._handle, _ptr(v), S, int(k), int(self.rand_seed), _ptr(out_ptr), _ptr(neighbors),
-                                 st))
+                                 _ptr(eid) if return_eid else c_void_p(0), st))
+        if return_eid:
+            return neighbors, counts, eid
         return neighbors, counts
 
     # -- Quiver.reindex_single(inputs, outputs, counts) -------------------------------------------------------------
@@ -155,6 +179,16 @@ class Quiver:
 
     # -- Quiver.sample_sub(stream_num, vertices, k) -----------------------------------------------------------------
     def sample_sub(self, stream_num, vertices, k):
+        """sample_neighbor + reindex_single fused (quiver_sample.cu:257-304): ONE C call (a one-hop qv_khop) and one host
+        synchronisation; k = -1 (no static bound) takes the two calls."""
+        if int(k) >= 0 and vertices.numel() > 0:
+            try:
+                n_id, hops = self.sample_khop(vertices, [int(k)])
+            except Unsupported:
+                pass
+            else:
+                edge_index = hops[0][0]
+                return n_id, edge_index[1], edge_index[0]  # (frontier, row_idx, col_idx)
         out, cnt = self.sample_neighbor(stream_num, vertices, k)
         return self.reindex_single(vertices, out, cnt)
 
@@ -167,7 +201,7 @@ class Quiver:
                                        _stream(self.device)))
 
     # -- fused k-hop (ours): every hop enqueued back to back, one host synchronisation --------------------------------
-    def sample_khop(self, seeds, sizes, gather=None):
+    def sample_khop(self, seeds, sizes, gather=None, with_eid=False):
         """All hops of GraphSageSampler.sample (sage_sampler.py:118-147) in one C call.
 
         Returns (n_id, [(edge_index[2, E_l], n_src_l, n_dst_l) for l in hops, innermost first]).
@@ -176,7 +210,12 @@ class Quiver:
 
         gather=(shard_tensor, feature_order or None): also gather the feature rows of n_id behind the last hop, without
         a host round trip in between (qv_khop_gather); returns (n_id, hops, x) with x = shard_tensor[feature_order[n_id]]
-        produced stream-ordered on the current stream.  x is a view of a buffer sized for the static frontier bound."""
+        produced stream-ordered on the current stream.  x is a VIEW of a buffer allocated before the frontier size is
+        known: min(S * prod(1 + size), node_count + S) rows (a frontier holds distinct nodes), at most
+        QUIVER_B200_FUSED_GATHER_MAX bytes (default 2 GiB, beyond that `Unsupported` -> callers take the two exact
+        calls).  The whole block stays alive while the caller holds x; `x = x.clone()` releases it.
+
+        with_eid=True: every hop tuple gains a 4th element, the e_id of its edges (CSR position or user edge id)."""
         v = _check_long_cuda(seeds, "seeds", self.device)
         n_hops = len(sizes)
         S = v.numel()
@@ -194,48 +233,61 @@ class Quiver:
             for h in range(n_hops):
                 offs.append(total)
                 total += max(2 * be[h], 2)
-            plan = (sz, bn[n_hops], offs, total, (c_void_p * n_hops)(), (c_int64 * (n_hops + 1))(), (c_int64 * n_hops)())
+            eoffs = []  # e_id regions (only allocated when asked for): appended behind the edge buffers
+            etotal = total
+            for h in range(n_hops):
+                eoffs.append(etotal)
+                etotal += max(be[h], 2)
+            plan = (sz, bn[n_hops], offs, total, (c_void_p * n_hops)(), (c_int64 * (n_hops + 1))(), (c_int64 * n_hops)(),
+                    eoffs, etotal, (c_void_p * n_hops)())
             if len(self._khop_plans) > 64:
                 self._khop_plans.clear()
             self._khop_plans[key] = plan
-        sz, n_id_cap, offs, total, buf_ptrs, out_nodes, out_edges = plan
-        arena = torch.empty(total, dtype=torch.int64, device=v.device)
+        sz, n_id_cap, offs, total, buf_ptrs, out_nodes, out_edges, eoffs, etotal, eid_ptrs = plan
+        arena = torch.empty(etotal if with_eid else total, dtype=torch.int64, device=v.device)
         base = arena.data_ptr()
         for h in range(n_hops):
             buf_ptrs[h] = base + 8 * offs[h]
+            if with_eid:
+                eid_ptrs[h] = base + 8 * eoffs[h]
+        eid_arg = eid_ptrs if with_eid else None
         x = None
         if gather is None:
             check(lib.qv_khop(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs,
-                              out_nodes, out_edges, _stream(self.device)))
+                              eid_arg, out_nodes, out_edges, _stream(self.device)))
         else:
             store, feature_order = gather
             if torch.cuda.current_device() != self.device:
                 raise RuntimeError("sample_khop(gather=...) must run with the sampler's device current")
             table, dtype, row_shape, row_bytes = store._gather_plan(self.device)
-            if max(n_id_cap, 1) * row_bytes > _FUSED_GATHER_MAX_BYTES:
+            x_rows = max(min(n_id_cap, self.node_count + S), 1)
+            if x_rows * row_bytes > _FUSED_GATHER_MAX_BYTES:
                 # the output is sized for the STATIC frontier bound (the real size is not known when the gather is
                 # enqueued); beyond this the two separate calls, which allocate exactly, are the better trade
                 raise Unsupported(_lib.QV_ERR_UNSUPPORTED, "fused gather buffer would exceed QUIVER_B200_FUSED_GATHER_MAX")
             order_ptr = c_void_p(0)
             if feature_order is not None:
                 order_ptr = _ptr(_check_long_cuda(feature_order, "feature_order", self.device))
-            x = torch.empty([max(n_id_cap, 1)] + row_shape, dtype=dtype, device=v.device)
+            x = torch.empty([x_rows] + row_shape, dtype=dtype, device=v.device)
             check(lib.qv_khop_gather(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs,
-                                     byref(table), order_ptr, row_bytes, _ptr(x), int(store.gather_variant), out_nodes,
-                                     out_edges, _stream(self.device)))
+                                     eid_arg, byref(table), order_ptr, row_bytes, _ptr(x), x_rows,
+                                     int(store.gather_variant), out_nodes, out_edges, _stream(self.device)))
         hops = []
         for h in range(n_hops):
             E = out_edges[h]
-            hops.append((arena[offs[h]:offs[h] + 2 * E].view(2, E), out_nodes[h + 1], out_nodes[h]))
+            hop = (arena[offs[h]:offs[h] + 2 * E].view(2, E), out_nodes[h + 1], out_nodes[h])
+            hops.append(hop + (arena[eoffs[h]:eoffs[h] + E], ) if with_eid else hop)
         if gather is None:
             return arena[:out_nodes[n_hops]], hops
         return arena[:out_nodes[n_hops]], hops, x[:out_nodes[n_hops]]
 
 
 def device_quiver_from_csr_array(indptr, indices, edge_ids=None, device=0, cuda=False):
-    """torch_quiver.device_quiver_from_csr_array -- quiver_sample.cu:361-461.  `edge_ids` is accepted and ignored:
-    the reference plumbs it but every sampler returns an empty e_id (sage_sampler.py:143)."""
-    return Quiver(indptr, indices, device, cuda)
+    """torch_quiver.device_quiver_from_csr_array -- quiver_sample.cu:361-461.  `edge_ids` is used iff it holds one id per
+    edge (quiver_sample.cu:385-387); the reference then plumbs it and returns an empty e_id anyway
+    (sage_sampler.py:143) -- here it feeds the opt-in e_id outputs (sample_neighbor(return_eid=True),
+    sample_khop(with_eid=True))."""
+    return Quiver(indptr, indices, device, cuda, edge_ids)
 
 
 def cpu_quiver_from_csr_array(*_args, **_kwargs):
@@ -254,12 +306,37 @@ _ELEMENT_DTYPE = {1: torch.uint8, 2: torch.float16, 4: torch.float32, 8: torch.f
 
 import os as _os
 
-_FUSED_GATHER_MAX_BYTES = int(_os.environ.get("QUIVER_B200_FUSED_GATHER_MAX", str(8 << 30)))
+_FUSED_GATHER_MAX_BYTES = int(_os.environ.get("QUIVER_B200_FUSED_GATHER_MAX", str(2 << 30)))
 _PITCH_ALIGN = int(_os.environ.get("QUIVER_B200_PITCH_ALIGN", "16"))  # bytes; 64 aligns rows to DRAM access granules
 
 
 def _pitch_for(row_bytes):
     return (row_bytes + _PITCH_ALIGN - 1) // _PITCH_ALIGN * _PITCH_ALIGN
+
+
+class _RawDeviceMemory:
+    """__cuda_array_interface__ carrier: lets torch view memory the library owns (no copy, no ownership transfer)."""
+
+    def __init__(self, ptr, n_elems, typestr):
+        self.__cuda_array_interface__ = {"shape": (n_elems, ), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+_TYPESTR = {torch.float32: "<f4", torch.float16: "<f2", torch.float64: "<f8", torch.uint8: "|u1", torch.int32: "<i4",
+            torch.int64: "<i8", torch.int16: "<i2", torch.int8: "|i1"}
+
+
+def _device_view(ptr, rows, pitch, row_bytes, dtype, device, row_shape):
+    if rows == 0:
+        return torch.empty([0] + row_shape, dtype=dtype, device=f"cuda:{device}")
+    esz = torch.empty(0, dtype=dtype).element_size()
+    carrier_dtype = dtype if dtype in _TYPESTR else {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[esz]
+    with torch.cuda.device(device):
+        flat = torch.as_tensor(_RawDeviceMemory(ptr, rows * pitch // esz, _TYPESTR[carrier_dtype]), device=f"cuda:{device}")
+    if carrier_dtype != dtype:
+        flat = flat.view(dtype)
+    return flat.view(rows, pitch // esz)[:, :row_bytes // esz].unflatten(1, row_shape) if len(row_shape) != 1 else \
+        flat.view(rows, pitch // esz)[:, :row_bytes // esz]
 
 
 class ShardTensorItem:
@@ -281,11 +358,14 @@ class ShardTensorItem:
 
 
 class _Shard:
-    __slots__ = ("device", "ptr", "rows", "pitch", "owned", "ipc_opened", "host_tensor", "host_base", "shape")
+    __slots__ = ("device", "ptr", "rows", "pitch", "owned", "ipc_opened", "host_tensor", "host_base", "shape",
+                 "open_device")
 
-    def __init__(self, device, ptr, rows, pitch, owned=False, ipc_opened=False, host_tensor=None, shape=None):
+    def __init__(self, device, ptr, rows, pitch, owned=False, ipc_opened=False, host_tensor=None, shape=None,
+                 open_device=None):
         self.device, self.ptr, self.rows, self.pitch = device, ptr, rows, pitch
         self.owned, self.ipc_opened, self.host_tensor, self.shape = owned, ipc_opened, host_tensor, shape
+        self.open_device = open_device  # the device in whose context an IPC handle was opened (and must be closed)
         self.host_base = host_tensor.data_ptr() if (host_tensor is not None and ptr) else 0  # what we registered
 
 
@@ -314,7 +394,7 @@ class ShardTensor:
                 if sh.owned and sh.ptr:
                     lib.qv_free(sh.device, c_void_p(sh.ptr))
                 elif sh.ipc_opened and sh.ptr:
-                    lib.qv_ipc_close_handle(sh.device, c_void_p(sh.ptr))
+                    lib.qv_ipc_close_handle(sh.device if sh.open_device is None else sh.open_device, c_void_p(sh.ptr))
                 elif sh.host_base:
                     # a registration that outlives its memory poisons later cudaMemcpy calls on reused addresses
                     lib.qv_host_unregister(c_void_p(sh.host_base))
@@ -349,7 +429,9 @@ class ShardTensor:
 
     def _append_tensor(self, tensor, target_device):
         if tensor.is_cuda:
-            raise RuntimeError("tensor must be CPU tensor")  # CHECK_CPU, quiver_feature.cu:19,147
+            # extension: the reference refuses (CHECK_CPU, quiver_feature.cu:19,147), which caps a table at host-memory
+            # size; rows already in HBM are copied device-to-device into the shard
+            return self._append_device_tensor(tensor, target_device)
         tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
         self._admit(tensor.shape, tensor.element_size(), tensor.dtype)
         rows, row_bytes = tensor.shape[0], self._row_bytes()
@@ -369,6 +451,40 @@ class ShardTensor:
             self.shards.append(_Shard(-1, alias.value or 0, rows, row_bytes, host_tensor=tensor,
                                       shape=list(tensor.shape)))
 
+    def _append_device_tensor(self, tensor, target_device):
+        if target_device < 0:
+            raise RuntimeError("a CUDA tensor cannot become the pinned-host tier")
+        tensor = tensor if tensor.is_contiguous() else tensor.contiguous()
+        view = self.append_empty(tensor.shape[0], list(tensor.shape[1:]), tensor.dtype, target_device)
+        row_bytes = self._row_bytes()
+        pitch = self.shards[-1].pitch
+        src_dev = tensor.device.index
+        with torch.cuda.device(src_dev):
+            st = _stream(src_dev)
+            check(lib.qv_copy_rows_device(src_dev, c_void_p(self.shards[-1].ptr), pitch, _ptr(tensor), row_bytes, row_bytes,
+                                          tensor.shape[0], st))
+            torch.cuda.current_stream(src_dev).synchronize()
+        del view
+
+    def append_empty(self, rows, row_shape, dtype, target_device):
+        """Extension: create the next shard IN PLACE in `target_device`'s HBM and return a torch view of it
+        ([rows, *row_shape], row stride = the shard's 16-byte-aligned pitch) for the caller to fill on the device -- how
+        a table larger than host memory (mag240m: 750 GB over 8 GPUs) is built.  The shard owns the memory
+        (cudaMalloc: exportable over CUDA IPC); the view must not outlive the ShardTensor."""
+        rows = int(rows)
+        dtype_size = torch.empty(0, dtype=dtype).element_size()
+        self._admit([rows] + [int(d) for d in row_shape], dtype_size, dtype)
+        row_bytes = self._row_bytes()
+        pitch = _pitch_for(row_bytes)
+        if pitch % dtype_size:
+            raise RuntimeError("row pitch is not a multiple of the element size")
+        ptr = c_void_p()
+        check(lib.qv_malloc(target_device, max(rows * pitch, 16), byref(ptr)))
+        if target_device != self.device_ and can_device_access_peer(self.device_, target_device):
+            init_p2p([self.device_, target_device])
+        self.shards.append(_Shard(target_device, ptr.value, rows, pitch, owned=True, shape=[rows] + list(row_shape)))
+        return _device_view(ptr.value, rows, pitch, row_bytes, dtype, target_device, list(row_shape))
+
     def _append_item(self, item):
         self._admit(item.shape, item.element_size, _ELEMENT_DTYPE.get(int(item.element_size)))
         row_bytes = self._row_bytes()
@@ -377,7 +493,7 @@ class ShardTensor:
         # open in the context of the device that will dereference it (quiver_feature.cu:122-134)
         check(lib.qv_ipc_open_handle(self.device_, handle, byref(ptr)))
         self.shards.append(_Shard(int(item.device), ptr.value, int(item.shape[0]), _pitch_for(row_bytes),
-                                  ipc_opened=True, shape=list(item.shape)))
+                                  ipc_opened=True, shape=list(item.shape), open_device=self.device_))
 
     def adopt(self, other):
         """Move the (single) shard of another ShardTensor to the end of this one, keeping ownership of its memory

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "qv_free": (c_int, [c_int, c_void_p]),
     "qv_upload_rows": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
     "qv_memset": (c_int, [c_int, c_void_p, c_int, c_size_t]),
+    "qv_copy_rows_device": (c_int, [c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "qv_host_register": (c_int, [c_int, c_void_p, c_size_t, POINTER(c_void_p)]),
     "qv_host_unregister": (c_int, [c_void_p]),
     "qv_ipc_get_handle": (c_int, [c_int, c_void_p, c_void_p]),
@@ -60,15 +61,16 @@ PROTOTYPES = {
     "qv_sampler_create": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_void_p)]),
     "qv_sampler_destroy": (c_int, [c_void_p]),
     "qv_sample_count": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, POINTER(c_int64), c_void_p]),
-    "qv_sample_fill": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "qv_sampler_set_edge_ids": (c_int, [c_void_p, c_void_p]),
+    "qv_sample_fill": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "qv_reindex": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                            POINTER(c_int64), c_void_p]),
     "qv_khop_bounds": (c_int, [c_int64, POINTER(c_int64), c_int, POINTER(c_int64), POINTER(c_int64)]),
     "qv_khop": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_uint64, c_void_p, POINTER(c_void_p),
-                        POINTER(c_int64), POINTER(c_int64), c_void_p]),
+                        POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "qv_khop_gather": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_uint64, c_void_p, POINTER(c_void_p),
-                               POINTER(ShardTable), c_void_p, c_int64, c_void_p, c_int, POINTER(c_int64),
-                               POINTER(c_int64), c_void_p]),
+                               POINTER(c_void_p), POINTER(ShardTable), c_void_p, c_int64, c_void_p, c_int64, c_int,
+                               POINTER(c_int64), POINTER(c_int64), c_void_p]),
     "qv_sampler_set_fast": (c_int, [c_void_p, c_int]),
     "qv_cal_neighbor_prob": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
 }
