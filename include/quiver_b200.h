@@ -72,6 +72,8 @@ QV_API int qv_init_p2p(const int *devices, int n_devices, int *n_enabled);
  * (quiver_feature.cu:166-174); these are the same two steps, exposed separately, plus the matching free the
  * reference never performs.  qv_upload_rows copies `rows` rows of `row_bytes` from host memory with source
  * pitch `src_pitch` into device memory with destination pitch `dst_pitch` (cudaMemcpy2D), synchronously. */
+/* qv_malloc rounds blocks of >= 2 MiB up to a 2 MiB multiple: peers read a block whose size is not a whole number of
+ * large pages up to 12x slower (60-105 vs 745 GB/s for random 1 KiB rows, profiles/r2_peer_alloc_granularity.txt). */
 QV_API int qv_malloc(int device, size_t bytes, void **dev_ptr);
 QV_API int qv_free(int device, void *dev_ptr);
 QV_API int qv_upload_rows(int device, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,

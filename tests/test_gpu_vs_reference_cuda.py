@@ -17,6 +17,7 @@ import torch
 from graphs import powerlaw_csr
 
 pytestmark = pytest.mark.gpu
+_KEEP = []
 
 
 @pytest.fixture(scope="module")
@@ -116,4 +117,7 @@ def test_gather_equals_reference_kernel(ref, dtype, d):
     assert got.dtype == want.dtype and got.shape == want.shape
     assert torch.equal(got.view(torch.uint8), want.view(torch.uint8))  # 0 ULP: byte identity
     assert torch.equal(got.cpu(), x[idx.cpu()])
-    theirs.unregister(cold_ref)
+    if dtype == torch.float32:
+        theirs.unregister(cold_ref)  # the reference reads data_ptr<float>() here (quiver_feature.cu:354-360): fp32 only
+    else:
+        _KEEP.append(cold_ref)       # a registration must not outlive its memory: keep the half tensor for the process

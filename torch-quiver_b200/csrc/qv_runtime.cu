@@ -5,6 +5,8 @@
 // and memory that can be freed.
 #include <unistd.h>
 
+#include <cstdlib>
+
 #include <mutex>
 #include <unordered_map>
 
@@ -129,6 +131,14 @@ int qv_malloc(int device, size_t bytes, void **dev_ptr)
     QV_REQUIRE(dev_ptr != nullptr, "qv_malloc: dev_ptr is NULL");
     *dev_ptr = nullptr;
     DeviceGuard g(device);
+    // Blocks of >= 2 MiB are rounded UP to a multiple of 2 MiB.  Measured on 2 x B200 (profiles/peer_probe2.py,
+    // profiles/r2_peer_alloc_granularity.txt): a peer GPU gathers random 1 KiB rows out of a 51.2e9-byte cudaMalloc block at
+    // 105 GB/s and out of a (40 GiB + 1 KiB) block at 60 GB/s -- but out of an exact 40 GiB block, or the first block padded
+    // to a 2 MiB multiple, at 745 GB/s.  The driver maps a block for peers with large pages only when its size is a whole
+    // number of them; otherwise the reader's address translation misses on nearly every row.  Local reads do not care.
+    static const size_t granule = getenv("QV_MALLOC_GRANULE") ? static_cast<size_t>(atoll(getenv("QV_MALLOC_GRANULE")))
+                                                                : (size_t(2) << 20);
+    if (granule > 1 && bytes >= (size_t(2) << 20)) bytes = (bytes + granule - 1) / granule * granule;
     QV_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 16));
     return QV_OK;
 }

@@ -159,6 +159,18 @@ class Feature(object):
         self._attach_cpu_part()
         return self
 
+    @classmethod
+    def from_tiered_store(cls, rank, store, feature_order=None, csr_topo=None):
+        """Extension: wrap a table that was built in place on the devices (quiver.shard_tensor.build_tiered_inplace: hot
+        prefix replicated per GPU, remainder striped over the NVLink clique, cold suffix in pinned host memory) as a
+        Feature.  `feature_order[id]` = storage row of original id (degree / access-probability order), applied inside
+        the gather kernel as for from_cpu_tensor."""
+        feature = cls(rank, [rank], 0, "p2p_clique_replicate", csr_topo)
+        feature.clique_tensor_list[feature.topo.get_clique_id(rank)] = store
+        feature.cpu_part = store.cpu_tensor
+        feature.feature_order = feature_order
+        return feature
+
     def set_local_order(self, local_order):
         """`local_order[i]` = original id of stored row i  =>  feature_order = its inverse (feature.py:283-294)."""
         local_range = torch.arange(end=local_order.size(0), dtype=torch.int64, device=self.rank)

@@ -198,3 +198,113 @@ def build_from_ranks(local_rows, device, group=None, cpu_part=None):
         st.shard_tensor.append(cpu_part, -1)
     dist.barrier(group)  # nobody gathers before every peer mapping exists
     return st
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Tiered placement built IN PLACE on the devices (tables larger than host memory; SURVEY 8(e) / north_star):
+#   [ hot prefix: replicated on every GPU | striped remainder: one contiguous block per GPU, read over NVLink |
+#     cold suffix: ONE pinned host copy shared by all ranks, read zero-copy over PCIe ]
+# The reference builds the same three tiers from a CPU tensor (feature.py:219-281: device_replicate /
+# p2p_clique_replicate + cpu_part); here every tier is filled where it lives, so no rank ever holds the whole table.
+# ----------------------------------------------------------------------------------------------------------------------
+def _fill_chunked(view, lo, fill, chunk_elems=1 << 26):
+    row_elems = 1
+    for d in view.shape[1:]:
+        row_elems *= int(d)
+    chunk_rows = max(1024, chunk_elems // max(1, row_elems))  # bounds the scratch a fill callback needs per call
+    for a in range(0, view.shape[0], chunk_rows):
+        b = min(a + chunk_rows, view.shape[0])
+        fill(view[a:b], lo + a, lo + b)
+
+
+def build_tiered_inplace(device, n_rows, row_shape, dtype, fill, hot_rows=0, cold_rows=0, group=None,
+                         broadcast_hot=True, shm_tag=None):
+    """Create an [n_rows, *row_shape] table over the ranks of `group` (None / uninitialised = this process alone).
+
+    `fill(view, lo, hi)` must write storage rows [lo, hi) into the CUDA tensor `view` ([hi-lo, *row_shape], possibly
+    row-strided).  Layout in storage-row order (callers map original ids to storage rows with a `feature_order` array):
+      rows [0, H)                  H = hot_rows: a full copy in EVERY rank's HBM (rank 0 fills it, NCCL broadcasts it
+                                   when `broadcast_hot`: "NCCL used only for the initial shard broadcast")
+      rows [H, n - C)              striped: rank r owns the r-th of `world` equal contiguous blocks (last takes the rest),
+                                   peers map it through CUDA IPC and read it one-sidedly inside the gather kernel
+      rows [n - C, n)              C = cold_rows: one pinned host copy in POSIX shared memory, registered by every rank
+    Returns (ShardTensor, info dict with the row ranges and this rank's stripe)."""
+    import os
+    import torch.distributed as dist
+    use_dist = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if use_dist else 0
+    world = dist.get_world_size(group) if use_dist else 1
+    H, C = int(hot_rows), int(cold_rows)
+    assert 0 <= H and 0 <= C and H + C <= n_rows
+    if world == 1:
+        H = 0  # a single GPU holds everything that is not cold: one shard
+    mid = n_rows - H - C
+    per = mid // world
+    lo = H + rank * per
+    hi = H + (rank + 1) * per if rank < world - 1 else n_rows - C
+    st = ShardTensor(device, ShardTensorConfig({}))
+    raw = st.shard_tensor
+    with torch.cuda.device(device):
+        if H > 0:
+            hot = raw.append_empty(H, row_shape, dtype, device)
+            if rank == 0 or not broadcast_hot:
+                _fill_chunked(hot, 0, fill)
+            if broadcast_hot and use_dist:
+                torch.cuda.synchronize()
+                step = max(1, (1 << 30) // max(1, hot.stride(0) * hot.element_size()))
+                for a in range(0, H, step):  # pitched rows: broadcast chunk by chunk through a dense staging buffer
+                    chunk = hot[a:a + step]
+                    if chunk.is_contiguous():
+                        dist.broadcast(chunk, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                    else:
+                        dense = chunk.contiguous()
+                        dist.broadcast(dense, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+                        chunk.copy_(dense)
+        local = torch_qv.ShardTensor(device)
+        mine = local.append_empty(hi - lo, row_shape, dtype, device)
+        _fill_chunked(mine, lo, fill)
+        torch.cuda.synchronize()
+    if use_dist:
+        items = exchange_shard_items(local.share_ipc()[0].share_ipc(), group)
+    else:
+        items = [None]
+    for r in range(world):
+        if r == rank:
+            raw.adopt(local)
+        else:
+            item = torch_qv.ShardTensorItem()
+            item.from_ipc(items[r])
+            raw.append(item)
+    cold = None
+    if C > 0:
+        row_elems = 1
+        for d in row_shape:
+            row_elems *= int(d)
+        if world == 1:
+            cold = torch.empty([C] + list(row_shape), dtype=dtype)
+        else:
+            tag = shm_tag or f"qv_cold_{os.environ.get('MASTER_PORT', '0')}_{n_rows}_{C}"
+            path = os.path.join("/dev/shm", tag)
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(C * row_elems * torch.empty(0, dtype=dtype).element_size())
+            dist.barrier(group)
+            cold = torch.from_file(path, shared=True, size=C * row_elems, dtype=dtype).view([C] + list(row_shape))
+        if rank == 0:
+            with torch.cuda.device(device):
+                step = max(1, (256 << 20) // max(1, row_elems * cold.element_size()))
+                for a in range(0, C, step):
+                    b = min(a + step, C)
+                    tmp = torch.empty([b - a] + list(row_shape), dtype=dtype, device=f"cuda:{device}")
+                    fill(tmp, n_rows - C + a, n_rows - C + b)
+                    cold[a:b].copy_(tmp)
+        if use_dist:
+            dist.barrier(group)
+            if rank == 0 and world > 1:
+                os.unlink(path)  # every rank holds its mapping; the name can go
+        st.cpu_tensor = cold
+        raw.append(cold, -1)
+    if use_dist:
+        dist.barrier(group)  # nobody gathers before every peer mapping exists and every tier is filled
+    info = {"hot": (0, H), "stripe": (lo, hi), "striped": (H, n_rows - C), "cold": (n_rows - C, n_rows), "world": world}
+    return st, info

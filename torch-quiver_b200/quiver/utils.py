@@ -129,7 +129,7 @@ def reindex_by_config(adj_csr: CSRTopo, graph_feature, gpu_portion):
     """Degree-descending row order with the hot `gpu_portion` prefix shuffled so clique shards are load balanced
     (reference: utils.py:229-241).  Returns (permuted feature, new_order) with feature_new[new_order[i]] == feature[i]."""
     n = adj_csr.node_count
-    by_degree = torch.argsort(adj_csr.degree, descending=True, stable=False)
+    by_degree = torch.argsort(adj_csr.degree.cpu(), descending=True, stable=False)  # (a CSRTopo may hold device tensors)
     hot = int(n * gpu_portion)
     by_degree[:hot] = by_degree[:hot][torch.randperm(hot)]
     inverse = torch.empty_like(by_degree)

@@ -310,6 +310,11 @@ _FUSED_GATHER_MAX_BYTES = int(_os.environ.get("QUIVER_B200_FUSED_GATHER_MAX", st
 _PITCH_ALIGN = int(_os.environ.get("QUIVER_B200_PITCH_ALIGN", "16"))  # bytes; 64 aligns rows to DRAM access granules
 
 
+def _alloc_bytes(nbytes):
+    """qv_malloc rounds every block of >= 2 MiB up to a 2 MiB multiple itself (peer page size, see quiver_b200.h)."""
+    return max(int(nbytes), 16)
+
+
 def _pitch_for(row_bytes):
     return (row_bytes + _PITCH_ALIGN - 1) // _PITCH_ALIGN * _PITCH_ALIGN
 
@@ -438,7 +443,7 @@ class ShardTensor:
         if target_device >= 0:
             pitch = _pitch_for(row_bytes)
             ptr = c_void_p()
-            check(lib.qv_malloc(target_device, max(rows * pitch, 16), byref(ptr)))
+            check(lib.qv_malloc(target_device, _alloc_bytes(rows * pitch), byref(ptr)))
             check(lib.qv_upload_rows(target_device, ptr, pitch, _ptr(tensor), row_bytes, row_bytes, rows))
             if target_device != self.device_ and can_device_access_peer(self.device_, target_device):
                 init_p2p([self.device_, target_device])
@@ -479,7 +484,7 @@ class ShardTensor:
         if pitch % dtype_size:
             raise RuntimeError("row pitch is not a multiple of the element size")
         ptr = c_void_p()
-        check(lib.qv_malloc(target_device, max(rows * pitch, 16), byref(ptr)))
+        check(lib.qv_malloc(target_device, _alloc_bytes(rows * pitch), byref(ptr)))
         if target_device != self.device_ and can_device_access_peer(self.device_, target_device):
             init_p2p([self.device_, target_device])
         self.shards.append(_Shard(target_device, ptr.value, rows, pitch, owned=True, shape=[rows] + list(row_shape)))
