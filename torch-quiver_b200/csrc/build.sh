@@ -10,7 +10,11 @@ objs=()
 pids=()
 for f in qv_runtime qv_xorwow qv_sample qv_gather; do
   src="$HERE/$f.cu"; obj="$HERE/build/$f.o"
-  if [[ ! -f "$obj" || "$src" -nt "$obj" || "$HERE/qv_common.cuh" -nt "$obj" || "$HERE/qv_xorwow.cuh" -nt "$obj" || "$ROOT/include/quiver_b200.h" -nt "$obj" ]]; then
+  stale=0
+  for dep in "$src" "$HERE"/*.cuh "$ROOT/include/quiver_b200.h"; do
+    if [[ ! -f "$obj" || "$dep" -nt "$obj" ]]; then stale=1; fi
+  done
+  if [[ $stale == 1 ]]; then
     "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden \
       -I"$ROOT/include" "$@" -c "$src" -o "$obj" &
     pids+=($!)

@@ -25,6 +25,7 @@
 //     nothing is rebuilt or cleared per hop; the dependent kernels are chained with programmatic dependent launch;
 //   * int64 ids and 64-bit sizes throughout (the reference truncates to int in several places).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 
@@ -1254,6 +1255,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+#include "qv_hop_kernels.cuh"
+
 __global__ void __launch_bounds__(256)
     max_degree_kernel(const int64_t *__restrict__ indptr, int64_t n_nodes, unsigned long long *__restrict__ result)
 {
@@ -1397,6 +1400,9 @@ struct qv_sampler {
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+    Buffer ctl;       // control words of the two-kernels-per-hop path (heavy list, tile descriptors, barrier counters)
+    Buffer tgt;       // int32[E]: target row of every sampled edge of the current hop (two-kernels-per-hop path)
+    Buffer tile_base; // int64[tiles]: output offset of every 64-row tile of the next hop (written by hop_reindex_kernel)
     Buffer fr_meta;   // [2][bound] int64: CSR row start / degree of every frontier node (fused k-hop path)
     Buffer node_map;  // MapWord per graph node: epoch-tagged first-occurrence map of the fused k-hop path
     unsigned int map_epoch = 0;  // 0 = the map has never been initialised
@@ -1674,6 +1680,8 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
         const char *env = getenv("QV_PDL_EARLY");
         const int early = (env && env[0] == '0') ? 0 : 1;
         cudaMemcpyToSymbol(g_pdl_early, &early, sizeof early);
+        const int hop_dbg = getenv("QV_HOP_DEBUG") ? atoi(getenv("QV_HOP_DEBUG")) : 0;
+        cudaMemcpyToSymbol(g_hop_debug, &hop_dbg, sizeof hop_dbg);
     }
     *out = s;
     return QV_OK;
@@ -1696,6 +1704,9 @@ int qv_sampler_destroy(qv_sampler *s)
     s->recip.release();
     s->node_map.release();
     s->fr_meta.release();
+    s->ctl.release();
+    s->tgt.release();
+    s->tile_base.release();
     if (s->d_meta) cudaFree(s->d_meta);
     if (s->h_meta) cudaFreeHost(s->h_meta);
     if (s->meta_ready) cudaEventDestroy(s->meta_ready);
@@ -1966,6 +1977,186 @@ int khop_run(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *size
     return QV_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two kernels per hop (qv_hop_kernels.cuh): hop_sample_kernel + hop_reindex_kernel.  Applies when every fan-out is in
+// [0, 32], the generator is the reference's (not the opt-in fast sampler) and every hop's item bound fits one
+// co-resident reindex grid; anything else takes khop_run (round 1's chain of single-purpose kernels).
+// ------------------------------------------------------------------------------------------------------------------
+int blocks_per_sm(const void *kernel, int threads, size_t smem)
+{
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        v = 0;
+    }
+    return v;
+}
+
+struct ReindexPlan {
+    int items = 0;  // items per thread (template argument); 0 = does not fit
+    int grid = 0;
+};
+
+ReindexPlan plan_reindex(qv_sampler *s, int64_t items_bound)
+{
+    // grid: one 512-thread block per 512 items of the BOUND, at most two blocks per SM (all resident: the kernel uses grid
+    // barriers); items per thread: what the bound then needs, rounded up to an instantiated size
+    static int per_sm = -1;
+    if (per_sm < 0) per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_reindex_kernel<16>), kReindexThreads, 0);
+    ReindexPlan p;
+    const int64_t cap = std::min<int64_t>(int64_t(std::min(per_sm, 2)) * s->n_sm, kReindexMaxBlocks);
+    if (cap <= 0) return p;
+    const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(cap, (items_bound + kReindexThreads - 1) / kReindexThreads));
+    const int64_t need = (((items_bound + grid - 1) / grid) + kReindexThreads - 1) / kReindexThreads;
+    for (int c : {1, 2, 4, 8, 16})
+        if (need <= c) {
+            p.items = c;
+            p.grid = static_cast<int>(grid);
+            return p;
+        }
+    return p;
+}
+
+bool fused_hops_apply(qv_sampler *s, int64_t S, const int64_t *sizes, int n_hops, const int64_t *bn, const int64_t *be)
+{
+    static const bool off = getenv("QV_KHOP_FUSED") && getenv("QV_KHOP_FUSED")[0] == '0';  // A-B switch
+    if (off || s->fast) return false;
+    for (int h = 0; h < n_hops; h++) {
+        if (sizes[h] < 0 || sizes[h] > 32) return false;
+        const ReindexPlan plan = plan_reindex(s, be[h] + (h == 0 ? S : 0));
+        if (plan.items == 0) return false;
+        if (h + 1 < n_hops) {  // the reindex kernel of hop h scans the next hop's tiles, at most kReindexTilesPerBlock per block
+            const int64_t tiles_next = (bn[h + 1] + kSampleTile - 1) / kSampleTile;
+            if ((tiles_next + plan.grid - 1) / plan.grid > kReindexTilesPerBlock) return false;
+        }
+        if ((bn[h] + kSampleTile - 1) / kSampleTile >= (int64_t(1) << 30)) return false;
+    }
+    return true;
+}
+
+int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
+                   int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, const int64_t *bn, const int64_t *be,
+                   cudaStream_t st, bool *id_error, const GatherTail &tail)
+{
+    int64_t *nbr = static_cast<int64_t *>(s->nbr.ptr);
+    int32_t *tgt = static_cast<int32_t *>(s->tgt.ptr);
+    MapWord *map = static_cast<MapWord *>(s->node_map.ptr);
+    int64_t *d_err = s->d_meta + kMetaErr;
+    *id_error = false;
+    if (s->map_epoch == 0 || s->map_epoch >= 0xFFFFFFF0u) {  // first use, or the 32-bit epoch is about to wrap
+        QV_CUDA(cudaMemsetAsync(map, 0xFF, static_cast<size_t>(std::max<int64_t>(s->n_nodes, 1)) * sizeof(MapWord), st));
+        s->map_epoch = 0;
+    }
+    s->map_epoch++;
+    const unsigned int epoch_hi = 0xFFFFFFFFu - s->map_epoch;
+    if (s->err_dirty) {
+        QV_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int64_t), st));
+        s->err_dirty = false;
+    }
+    // control words: [heavy list | per hop: ticket, barrier counter, block counts, tile descriptors]
+    int64_t max_tiles = 1;
+    for (int h = 0; h < n_hops; h++) max_tiles = std::max(max_tiles, (bn[h] + kSampleTile - 1) / kSampleTile);
+    const size_t stride = (static_cast<size_t>(kHopCtlFixed + max_tiles) + 7) & ~size_t(7);
+    const size_t ctl_words = kCtlHeader + stride * n_hops;
+    unsigned long long *ctl = static_cast<unsigned long long *>(s->ctl.ptr);
+    QV_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * sizeof(unsigned long long), st));
+
+    int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start + bn[n_hops];
+    static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 8>), kSampleWarps * 32, 0);
+    for (int h = 0; h < n_hops; h++) {
+        int64_t *m = s->d_meta + kMetaStride * h;
+        unsigned long long *hop = ctl + kCtlHeader + stride * h;
+        const int k = static_cast<int>(sizes[h]);
+        const uint32_t *states = nullptr;
+        QV_TRY(rng_states_for(s, rand_seed, h == 0 ? S : 0, h == 0 ? nullptr : m + kMetaS, bn[h], st, &states));
+        HopSampleArgs a;
+        memset(&a, 0, sizeof a);
+        a.indptr = s->indptr;
+        a.indices = s->indices;
+        a.n_nodes = s->n_nodes;
+        a.seeds = h == 0 ? seeds : n_id;
+        a.S_arg = h == 0 ? S : 0;
+        a.d_S = h == 0 ? nullptr : m + kMetaS;
+        a.k = k;
+        a.rng_states = states;
+        a.rt = RecipTable{static_cast<const unsigned long long *>(s->recip.ptr), s->recip_n, 1u, 0xFFFFFFFFu};
+        a.out = nbr;
+        a.tgt = tgt;
+        a.eid_out = eid_buf ? eid_buf[h] : nullptr;
+        a.edge_ids = s->edge_ids;
+        a.cached_start = h == 0 ? nullptr : fr_start;
+        a.cached_deg = h == 0 ? nullptr : fr_deg;
+        a.desc = hop + kHopCtlFixed;
+        a.heavy = ctl;
+        a.d_E = m + kMetaE;
+        a.tile_base = h == 0 ? nullptr : static_cast<const int64_t *>(s->tile_base.ptr);
+        static const bool insert_in_reindex = getenv("QV_HOP_INSERT") && getenv("QV_HOP_INSERT")[0] == 'r';  // A-B switch
+        if (!insert_in_reindex) {
+            a.node_map = map;
+            a.epoch_hi = epoch_hi;
+            a.item_base = h == 0 ? S : 0;
+            a.d_err = d_err;
+        }
+        a.n_front = (h == 0 || s->max_degree <= kHeavyDeg) ? 0 : kHeavyListCap;
+        const int64_t tiles = (bn[h] + kSampleTile - 1) / kSampleTile;
+        const size_t smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max(k, 1) * 13;
+        a.ticket = (h == 0 && tiles > int64_t(sample_per_sm) * s->n_sm) ? hop : nullptr;  // only hop 0 looks back
+        QV_CUDA(launch_chained(hop_sample_kernel<4, 8>, static_cast<unsigned>(tiles + a.n_front), kSampleWarps * 32, smem, st, a));
+        QV_CHECK_LAUNCH("hop_sample_kernel");
+
+        HopReindexArgs r;
+        memset(&r, 0, sizeof r);
+        r.prefix = h == 0 ? seeds : nullptr;
+        r.P_arg = h == 0 ? S : 0;
+        r.nbr = nbr;
+        r.d_E = m + kMetaE;
+        r.map = map;
+        r.epoch_hi = epoch_hi;
+        r.insert_done = insert_in_reindex ? 0 : 1;
+        r.n_nodes = s->n_nodes;
+        r.d_F_prev = h == 0 ? nullptr : m + kMetaS;
+        r.frontier = n_id;
+        r.d_F = m + kMetaF;
+        r.d_next_S = m + kMetaStride + kMetaS;
+        r.indptr = s->indptr;
+        r.fr_start = h + 1 < n_hops ? fr_start : nullptr;
+        r.fr_deg = h + 1 < n_hops ? fr_deg : nullptr;
+        r.heavy = ctl;
+        r.tgt = tgt;
+        r.edge_buf = edge_buf[h];
+        r.bar = hop + 1;
+        r.agg = hop + 2;
+        r.d_err = d_err;
+        if (h + 1 < n_hops) {
+            r.tile_base_next = static_cast<int64_t *>(s->tile_base.ptr);
+            r.d_E_next = m + kMetaStride + kMetaE;
+            r.k_next = sizes[h + 1];
+        }
+        const ReindexPlan plan = plan_reindex(s, be[h] + (h == 0 ? S : 0));
+        switch (plan.items) {
+        case 1: QV_CUDA(launch_chained(hop_reindex_kernel<1>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 2: QV_CUDA(launch_chained(hop_reindex_kernel<2>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 4: QV_CUDA(launch_chained(hop_reindex_kernel<4>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 8: QV_CUDA(launch_chained(hop_reindex_kernel<8>, plan.grid, kReindexThreads, 0, st, r)); break;
+        default: QV_CUDA(launch_chained(hop_reindex_kernel<16>, plan.grid, kReindexThreads, 0, st, r)); break;
+        }
+        QV_CHECK_LAUNCH("hop_reindex_kernel");
+    }
+    QV_CUDA(cudaMemcpyAsync(s->h_meta, s->d_meta, kMetaWords * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    QV_CUDA(cudaEventRecord(s->meta_ready, st));
+    if (tail.table) {
+        const int64_t *d_n = s->d_meta + kMetaStride * (n_hops - 1) + kMetaF;
+        QV_TRY(gather_enqueue(tail.table, n_id, tail.feature_order, std::min(bn[n_hops], tail.capacity_rows), d_n,
+                              tail.row_bytes, tail.features, tail.variant, st));
+    }
+    QV_CUDA(cudaEventSynchronize(s->meta_ready));
+    if (s->h_meta[kMetaErr] != 0) {
+        *id_error = true;  // the caller redoes the call on the hash path
+        s->err_dirty = true;
+    }
+    return QV_OK;
+}
+
 int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *sizes, int n_hops, uint64_t rand_seed,
                int64_t *n_id, int64_t *const *edge_buf, int64_t *const *eid_buf, int64_t *out_nodes, int64_t *out_edges,
                qv_stream_t stream, const GatherTail &tail);
@@ -2045,6 +2236,15 @@ int khop_entry(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t *si
         s->fr_meta.release();
 
     bool id_error = false;
+    if (use_map && s->fr_meta.ptr && fused_hops_apply(s, S, sizes, n_hops, bn, be)) {
+        int64_t max_tiles = 1;
+        for (int h = 0; h < n_hops; h++) max_tiles = std::max(max_tiles, (bn[h] + kSampleTile - 1) / kSampleTile);
+        const size_t stride = (static_cast<size_t>(kHopCtlFixed + max_tiles) + 7) & ~size_t(7);
+        QV_TRY(s->ctl.ensure((kCtlHeader + stride * n_hops) * sizeof(unsigned long long)));
+        QV_TRY(s->tgt.ensure(static_cast<size_t>(std::max<int64_t>(max_edges, 1)) * sizeof(int32_t)));
+        QV_TRY(s->tile_base.ensure(static_cast<size_t>(max_tiles) * sizeof(int64_t)));
+        QV_TRY(khop_run_fused(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, bn, be, st, &id_error, tail));
+    } else
     QV_TRY(khop_run(s, seeds, S, sizes, n_hops, rand_seed, n_id, edge_buf, eid_buf, bn, be, use_map, st, &id_error, tail));
     if (id_error) {
         QV_TRY(ensure_table(s, bn[n_hops]));
