@@ -83,6 +83,7 @@ struct HopSampleArgs {
     unsigned long long *heavy;   // ctl[0..]: count + listed rows
     int64_t *d_E;                // out: number of sampled edges of the hop
     int n_front;                 // heavy blocks at the front of the grid (0 on hop 0: the list is still empty)
+    int release_early;           // the grid leaves room on every SM: the reindex kernel's blocks may become resident at once
 };
 
 struct __align__(16) TileSmem {
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kern
     __shared__ StreamSmem ss;
     __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp];
     pdl_wait();  // everything this hop reads (frontier, CSR rows, sizes, heavy list) is the previous kernel's output
+    if (a.release_early) pdl_release();
     const int64_t S = dev_size(a.S_arg, a.d_S);
     const int64_t n_tiles = (S + kSampleTile - 1) / kSampleTile;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -569,9 +571,6 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
     __shared__ uint32_t tsum[kReindexTilesPerBlock];
     pdl_wait();
     pdl_release();  // the next kernel's blocks may become resident (they park in their own wait): this grid already is
-    const bool dbg = g_hop_debug && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && threadIdx.x == 0;
-    unsigned long long ts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (dbg) ts[0] = global_ns();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t P = a.prefix ? a.P_arg : 0, E = *a.d_E;
     const int64_t n = P + E;
@@ -607,9 +606,7 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
         }
     }
     if (bad) *a.d_err = 1;
-    if (dbg) ts[1] = global_ns();
     if (!a.insert_done) grid_barrier(a.bar, bar_target += G);
-    if (dbg) ts[2] = global_ns();
 
     // ---- phase 2: first occurrences, counted in item order --------------------------------------------------------------------
     // col[j]: the item's local id if its node is already in the frontier (payload < 2^31), else the candidate word -- such an
@@ -651,9 +648,7 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
         for (int j = 0; j < kItems; j++) tot += rowtot[j];
         __stcg(a.agg + blockIdx.x, tot);
     }
-    if (dbg) ts[3] = global_ns();
     grid_barrier(a.bar, bar_target += G);
-    if (dbg) ts[4] = global_ns();
 
     {  // offset of this block = sum of the counts of the blocks in front of it; everybody also learns the grand total
         long long s = 0, all = 0;
@@ -688,38 +683,41 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
     const long long F = F_prev + grand_total_sh;
     {
         long long row_base = F_prev + block_base_sh;
-        long long rs[kItems], rd[kItems];
+        constexpr int kBatch = kItems < 4 ? kItems : 4;  // CSR rows of the new nodes: four items' loads in flight at a time
 #pragma unroll
-        for (int j = 0; j < kItems; j++) {  // the new nodes' CSR rows: all loads first
-            rs[j] = rd[j] = 0;
-            if (a.fr_start && (first_mask >> j & 1u)) {
-                rs[j] = a.indptr[key[j]];
-                rd[j] = a.indptr[key[j] + 1];
-            }
-        }
+        for (int j0 = 0; j0 < kItems; j0 += kBatch) {
+            long long rs[kBatch], rd[kBatch];
 #pragma unroll
-        for (int j = 0; j < kItems; j++) {
-            if (first_mask >> j & 1u) {
-                const long long local = row_base + wex[j][warp] + lt_count[j];
-                col[j] = static_cast<unsigned int>(local);
-                a.frontier[local] = key[j];
-                __stcg(&a.map[key[j]], map_word(a.epoch_hi, static_cast<unsigned int>(local)));
-                if (a.fr_start) {
-                    const long long deg = rd[j] - rs[j];
-                    a.fr_start[local] = rs[j];
-                    a.fr_deg[local] = deg;
-                    if (deg > kHeavyDeg) {
-                        const unsigned long long at = atomicAdd(a.heavy, 1ull);
-                        if (at < kHeavyListCap) a.heavy[1 + at] = static_cast<unsigned long long>(local);
-                    }
+            for (int u = 0; u < kBatch; u++) {
+                rs[u] = rd[u] = 0;
+                if (a.fr_start && (first_mask >> (j0 + u) & 1u)) {
+                    rs[u] = a.indptr[key[j0 + u]];
+                    rd[u] = a.indptr[key[j0 + u] + 1];
                 }
             }
-            row_base += rowtot[j];
+#pragma unroll
+            for (int u = 0; u < kBatch; u++) {
+                const int j = j0 + u;
+                if (first_mask >> j & 1u) {
+                    const long long local = row_base + wex[j][warp] + lt_count[j];
+                    col[j] = static_cast<unsigned int>(local);
+                    a.frontier[local] = key[j];
+                    __stcg(&a.map[key[j]], map_word(a.epoch_hi, static_cast<unsigned int>(local)));
+                    if (a.fr_start) {
+                        const long long deg = rd[u] - rs[u];
+                        a.fr_start[local] = rs[u];
+                        a.fr_deg[local] = deg;
+                        if (deg > kHeavyDeg) {
+                            const unsigned long long at = atomicAdd(a.heavy, 1ull);
+                            if (at < kHeavyListCap) a.heavy[1 + at] = static_cast<unsigned long long>(local);
+                        }
+                    }
+                }
+                row_base += rowtot[j];
+            }
         }
     }
-    if (dbg) ts[5] = global_ns();
     grid_barrier(a.bar, bar_target += G);
-    if (dbg) ts[6] = global_ns();
 
     // ---- phase 3: edge_index ---------------------------------------------------------------------------------------------
 #pragma unroll
@@ -806,9 +804,4 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
             }
         }
     }
-    if (dbg)
-        printf("[hop_reindex<%d> block %d/%d n=%lld] keys+insert %.1f | bar %.1f | flags %.1f | bar %.1f | assign %.1f | bar %.1f | "
-               "emit+offsets %.1f us\n", kItems, blockIdx.x, gridDim.x, (long long)n, (ts[1] - ts[0]) * 1e-3, (ts[2] - ts[1]) * 1e-3,
-               (ts[3] - ts[2]) * 1e-3, (ts[4] - ts[3]) * 1e-3, (ts[5] - ts[4]) * 1e-3, (ts[6] - ts[5]) * 1e-3,
-               (global_ns() - ts[6]) * 1e-3);
 }

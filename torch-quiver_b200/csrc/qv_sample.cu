@@ -2101,6 +2101,9 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
         const int64_t tiles = (bn[h] + kSampleTile - 1) / kSampleTile;
         const size_t smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max(k, 1) * 13;
         a.ticket = (h == 0 && tiles > int64_t(sample_per_sm) * s->n_sm) ? hop : nullptr;  // only hop 0 looks back
+        // a grid of at most ~3 blocks per SM leaves registers and threads for the reindex kernel's two 512-thread blocks
+        static const bool early_off = getenv("QV_HOP_EARLY") && getenv("QV_HOP_EARLY")[0] == '0';
+        a.release_early = (!early_off && tiles + a.n_front <= int64_t(3) * s->n_sm) ? 1 : 0;
         QV_CUDA(launch_chained(hop_sample_kernel<4, 8>, static_cast<unsigned>(tiles + a.n_front), kSampleWarps * 32, smem, st, a));
         QV_CHECK_LAUNCH("hop_sample_kernel");
 
