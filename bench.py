@@ -12,7 +12,7 @@ Workloads (--config; BASELINE.json):
       (pareto(2) degrees, neighbours drawn in proportion to degree), 256-d fp32 features (1 KiB rows, 102 GB), 1024 seeds,
       fan-out [15,10,5].  N=1: whole table in one GPU's HBM.  N>1: every rank holds a CSR replica (the sampler does not
       shard) and the table is placed by ACCESS PROBABILITY (sample_prob -> storage order): the hottest
-      --hot-frac of the rows replicated on every GPU (NCCL broadcast at setup), the rest striped over the N GPUs and read
+      --hot-frac (default 40 %) of the rows replicated on every GPU (NCCL broadcast at setup), the rest striped over the N GPUs and read
       one-sidedly over NVLink inside the gather kernel; every rank runs its own batches (weak scaling, no data-path
       collective).
   c1  Reddit-shaped (232 965 nodes, mean degree 492, 602-d, fan-out [25,10]) -- configs[0], the reference's CPU-runnable case
@@ -45,6 +45,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "torch-quiver_b200"), os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
+
+# torch's caching allocator: every step returns fresh tensors whose sizes vary with the batch (n_id, edge_index, the gathered
+# rows: 0.1-1 GB); with unlimited splitting a large cached block gets carved up by a smaller request and the next large one
+# pays a cudaMalloc (13-33 ms next to a 100 GB table).  Blocks above 256 MB are kept whole (a documented PyTorch knob).
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "max_split_size_mb:256")
 
 import torch  # noqa: E402
 
@@ -560,6 +565,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     else:
         feature, fuse_target, feature_order, placement, info, x_cpu = build_feature(args, cfg, dev, rank, world, indptr,
                                                                                      indices if not args.uva else None, sampler)
+    feature._my_store().shard_tensor.gather_variant = args.gather_variant
     n_rep = max(1, args.repeats)
     n_batches = args.warmup + n_rep * args.steps
     batches_host = make_seed_batches(n_batches, n, batch, seed=1 + rank, legacy=cfg["legacy"])
@@ -570,6 +576,12 @@ def run_ours(args, cfg, rank, world, local_rank):
     setup_s = time.perf_counter() - t_setup
 
     # ---- warm-up -----------------------------------------------------------------------------------------------------
+    # torch's caching allocator first: `feature[n_id]` returns a fresh [rows, dim] tensor per call and rows varies per batch,
+    # so without two cached blocks of the largest possible size a step now and then pays a cudaMalloc (13-33 ms measured
+    # next to a 100 GB table) -- steady state for a training loop, noise for a 20-step timed region
+    cap_rows = min(batch * int(torch.tensor([1 + s_ for s_ in sizes]).prod()), n + batch)
+    _warm = [torch.empty(cap_rows, dim, device=dev) for _ in range(2)]
+    del _warm
     clocks = ClockSampler(local_rank)
     clocks.start()
     for b in batches_dev[:args.warmup]:
@@ -605,8 +617,14 @@ def run_ours(args, cfg, rank, world, local_rank):
     for i, b in enumerate(timed[0]):
         n_id, _, adjs = sampler.sample(b)
         ev[3 * i + 1].record()
+        th0 = time.perf_counter()
         res = feature[n_id]
+        th1 = time.perf_counter()
         ev[3 * i + 2].record()
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[dbg] step {i}: feature[n_id] host {1e3 * (th1 - th0):.3f} ms, then sync {1e3 * (time.perf_counter() - th1):.3f} ms, "
+                  f"rows {n_id.numel()}", file=sys.stderr)
         edges += sum(a.edge_index.shape[1] for a in adjs)
         hop_bytes += sum(40 * a.edge_index.shape[1] + 40 * int(a.size[1]) + 8 * int(a.size[0]) for a in adjs)
         rows += n_id.numel()
@@ -827,6 +845,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                                    if fused else "none: sampler and gather on one stream")),
                    "l2": f"inputs larger than L2 ({n_edges * 8 / 1e9:.1f} GB CSR + {n * row_bytes / 1e9:.1f} GB feature table vs "
                          "126 MB L2); fresh seeds every step and every repeat",
+                   "torch_allocator": os.environ.get("PYTORCH_CUDA_ALLOC_CONF"),
                    "edges_per_step": edges_all / args.steps / world, "rows_per_step": rows_all / args.steps / world,
                    "setup_s": setup_s},
         "spread": {"repeats": n_rep, "edges_per_s_min": mins.tolist()[0], "edges_per_s_max": mins.tolist()[1],
@@ -895,12 +914,14 @@ def main():
     ap.add_argument("--config", default=os.environ.get("QV_BENCH_CONFIG", "ns"), choices=sorted(CONFIGS))
     ap.add_argument("--repeats", type=int, default=3, help="timed K-step regions (distinct batches); value = median")
     ap.add_argument("--hot-frac", type=float, default=None,
-                    help="N>1: fraction of rows (hottest first) replicated on every GPU (default: 0.2; c3: 0; c4: 0.3; c5: 0)")
+                    help="N>1: fraction of rows (hottest first) replicated on every GPU (default: 0.4; c3: 0; c4: 0.3; c5: 0)")
     ap.add_argument("--cold-frac", type=float, default=None,
                     help="fraction of rows (coldest) kept in pinned host memory (default 0; c4 at N>1: 0.5)")
     ap.add_argument("--order", default="auto", choices=["auto", "prob", "degree", "none"],
                     help="storage order of the feature rows: access probability (sample_prob), degree, or original ids")
     ap.add_argument("--device-build", action="store_true", help="build small tables in place on the device too")
+    ap.add_argument("--feat-dim", type=int, default=None, help="override the config's feature width (experiments)")
+    ap.add_argument("--gather-variant", type=int, default=0, help="qv_gather variant: 0 auto, 1 SIMT, 2 TMA bulk copies")
     ap.add_argument("--uva", action="store_true", help="sampler mode UVA: indices in pinned host memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
@@ -910,9 +931,12 @@ def main():
     ap.add_argument("--overlap", action="store_true",
                     help="run the sampler on its own high-priority stream so sample(i+1) overlaps gather(i)")
     args = ap.parse_args()
-    cfg = CONFIGS[args.config]
+    cfg = dict(CONFIGS[args.config])
+    if args.feat_dim:
+        cfg["feat_dim"] = args.feat_dim
+        cfg["title"] += f" [feature width overridden: {args.feat_dim}]"
     if args.hot_frac is None:
-        args.hot_frac = {"c3": 0.0, "c4": 0.3, "c5": 0.0}.get(args.config, 0.2)
+        args.hot_frac = {"c3": 0.0, "c4": 0.3, "c5": 0.0}.get(args.config, 0.4)
     if args.cold_frac is None:
         args.cold_frac = 0.5 if args.config == "c4" else 0.0
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
