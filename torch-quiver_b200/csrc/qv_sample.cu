@@ -2062,6 +2062,14 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
     QV_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * sizeof(unsigned long long), st));
 
     int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start + bn[n_hops];
+    // 18 KB of static + a few KB of dynamic shared memory per 128-thread block: with the default carve-out the SM fits 4 such
+    // blocks (ncu: occupancy limit "shared mem 4" against "registers 8"); ask for the largest shared-memory carve-out instead
+    static const bool carve = [] {
+        cudaFuncSetAttribute(hop_sample_kernel<4, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaGetLastError();
+        return true;
+    }();
+    (void)carve;
     static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 8>), kSampleWarps * 32, 0);
     for (int h = 0; h < n_hops; h++) {
         int64_t *m = s->d_meta + kMetaStride * h;
