@@ -28,8 +28,13 @@
 constexpr int kHeavyDeg = 3072;     // rows with more neighbours join the call's heavy list (>= 96 draws per lane)
 constexpr int kHeavyListCap = 256;  // listed rows = heavy blocks at the front of every later hop's sampling grid
 constexpr int kStreamMin = 64;      // draws per lane from which a row of a heavy block is streamed to the tester warps
-constexpr int kStreamChunk = 32;    // draws per lane per ring buffer
-constexpr int kStreamBufs = 4;      // ring depth (named barriers 1..4 = full, 5..8 = empty, 9 = all draws evaluated)
+constexpr int kStreamChunk = 60;    // draws per lane per ring buffer (a multiple of kGenUnroll)
+constexpr int kGenUnroll = 10;      // generator steps per loop iteration (a multiple of 5 keeps the state rotation free of moves)
+constexpr int kHopTiles = 2;        // 64-row tiles per regular block
+constexpr int kHopWarps = kHopTiles * kSampleWarps;  // 8 warps: a heavy block is 1 generator warp + 7 tester warps
+constexpr int kHopThreads = kHopWarps * 32;
+constexpr int kTesters = kHopWarps - 2;  // warp 4 shares the generator's scheduler: it only joins the barriers (see stream_test)
+constexpr int kStreamBufs = 4;      // ring depth (named barriers 1..4 = full, 5..8 = empty, 9 = all draws evaluated; all of kHopThreads)
 
 // ---- control words of one fused k-hop call (zeroed by one memset) ----------------------------------------------------
 //   ctl[0]                 number of heavy rows listed so far (may exceed the cap: entries beyond it are dropped)
@@ -99,11 +104,13 @@ struct __align__(16) StreamSmem {
     uint32_t dchunk[kStreamBufs][32];             // each lane's Weyl counter at the start of the chunk
 };
 
-// Loads the CSR rows of tile b, caps the counts and scans them.  All 128 threads; two block barriers.
-__device__ __forceinline__ void tile_prologue(const HopSampleArgs &a, TileSmem &sm, int64_t S, int64_t b, bool publish)
+// Loads the CSR rows of tile b (by the 64 threads starting at `first_thread`), caps the counts and scans them (by the first
+// warp of those).  Called by ALL threads of the block: two block barriers.
+__device__ __forceinline__ void tile_prologue(const HopSampleArgs &a, TileSmem &sm, int64_t S, int64_t b, bool publish,
+                                              int first_thread)
 {
-    const int t = threadIdx.x;
-    if (t < kSampleTile) {
+    const int t = static_cast<int>(threadIdx.x) - first_thread;
+    if (t >= 0 && t < kSampleTile) {
         const int64_t r = b * kSampleTile + t;
         int64_t start = 0, deg = 0;
         if (r < S) {
@@ -129,7 +136,7 @@ __device__ __forceinline__ void tile_prologue(const HopSampleArgs &a, TileSmem &
         }
     }
     __syncthreads();
-    if (t < 32) {  // exclusive scan of the 64 capped counts, two per lane
+    if (t >= 0 && t < 32) {  // exclusive scan of the 64 capped counts, two per lane
         const uint32_t kk = static_cast<uint32_t>(a.k);
         const uint32_t c0 = min(sm.deg[2 * t], kk), c1 = min(sm.deg[2 * t + 1], kk);
         uint32_t incl = c0 + c1;
@@ -184,26 +191,39 @@ __device__ __forceinline__ uint32_t xorwow_raw(Xorwow &s)
 // Generator side of a streamed row: `rem` = this lane's draws in the row, n_chunks = chunks of lane 0 (the most).
 __device__ __noinline__ Xorwow stream_generate(Xorwow rng, uint32_t rem, uint32_t n_chunks, StreamSmem *ss, int lane)
 {
+    const bool prof = g_hop_debug == 4;
+    long long t_wait = 0, t_all = prof ? clock64() : 0;
     for (uint32_t c = 0; c < n_chunks; c++) {
         const int p = c % kStreamBufs;
-        named_bar_sync(1 + kStreamBufs + p, 128);  // the testers are done with this buffer (or primed it)
+        const long long w0 = prof ? clock64() : 0;
+        named_bar_sync(1 + kStreamBufs + p, kHopThreads);  // the testers are done with this buffer (or primed it)
+        if (prof) t_wait += clock64() - w0;
         ss->dchunk[p][lane] = rng.d;
         const uint32_t t0 = c * kStreamChunk;
         if (t0 + kStreamChunk <= rem) {
+            // rolled in steps of kGenUnroll: the whole loop stays in the instruction cache next to the tester sharing this
+            // warp's scheduler (a fully unrolled chunk is 7 KB of straight-line code)
+            uint32_t *dst = &ss->buf[p][0][lane];
+#pragma unroll 1
+            for (int t = 0; t < kStreamChunk; t += kGenUnroll) {
 #pragma unroll
-            for (int t = 0; t < kStreamChunk; t++) ss->buf[p][t][lane] = xorwow_raw(rng);
+                for (int u = 0; u < kGenUnroll; u++) dst[(t + u) * 32] = xorwow_raw(rng);
+            }
             rng.d += kStreamChunk * 362437u;
         } else {
             const uint32_t left = rem > t0 ? rem - t0 : 0;
             for (uint32_t t = 0; t < left; t++) ss->buf[p][t][lane] = xorwow_raw(rng);
             rng.d += left * 362437u;
         }
-        named_bar_arrive(1 + p, 128);
+        named_bar_arrive(1 + p, kHopThreads);
     }
+    if (prof && lane == 0 && n_chunks > 20)
+        printf("[stream generator] %u chunks of %d rounds: %lld cycles, %lld of them waiting for a free buffer\n", n_chunks,
+               kStreamChunk, (long long)(clock64() - t_all), t_wait);
     return rng;
 }
 
-// Tester side (warps 1..3 of a heavy block, q = 0..2): the same sequence of streamed rows, derived from the tile's degrees.
+// Tester side (warps 1..7 of a heavy block, q = 0..6): the same sequence of streamed rows, derived from the tile's degrees.
 __device__ __noinline__ void stream_test(const HopSampleArgs a, const TileSmem *sm, int w, int q, int lane,
                                          uint32_t *slots_w, uint32_t kcap, StreamSmem *ss)
 {
@@ -216,41 +236,42 @@ __device__ __noinline__ void stream_test(const HopSampleArgs a, const TileSmem *
         if (rem0 < kStreamMin) continue;
         uint32_t *srow = slots_w + static_cast<size_t>(i) * kcap;
         const uint32_t n_chunks = (rem0 + kStreamChunk - 1) / kStreamChunk;
-        // This warp evaluates rounds q, q + 3, ... of every chunk with the plain `%` operator: no table walk (a streamed row
+        // This warp evaluates rounds q, q + 7, ... of every chunk with the plain `%` operator: no table walk (a streamed row
         // would read its own cold stretch of the reciprocal table, and holding two chunks of 64-bit reciprocals in registers
         // spills under the kernel's 64-register budget -- both measured slower).  All shared-memory reads of the chunk come
         // BEFORE the first reservoir update: the updates are shared-memory atomics through a generic pointer and the compiler
         // keeps every later load behind a possible earlier store, which serialises the eleven divisions otherwise.
-        constexpr int kPer = (kStreamChunk + 2) / 3;
+        constexpr int kPer = (kStreamChunk + kTesters - 1) / kTesters;
 #pragma unroll
         for (int p = 0; p < kStreamBufs; p++)  // every buffer starts empty
-            if (static_cast<uint32_t>(p) < n_chunks) named_bar_arrive(1 + kStreamBufs + p, 128);
+            if (static_cast<uint32_t>(p) < n_chunks) named_bar_arrive(1 + kStreamBufs + p, kHopThreads);
         for (uint32_t c = 0; c < n_chunks; c++) {
             const int p = c % kStreamBufs;
-            named_bar_sync(1 + p, 128);
+            named_bar_sync(1 + p, kHopThreads);
             const uint32_t d0 = ss->dchunk[p][lane];
             uint32_t rr[kPer], num[kPer];
 #pragma unroll
             for (int u = 0; u < kPer; u++) {
-                const int t = q + 3 * u;
-                rr[u] = t < kStreamChunk ? ss->buf[p][t][lane] + d0 + static_cast<uint32_t>(t + 1) * 362437u : 0u;
+                const int t = q + kTesters * u;
+                rr[u] = (q >= 0 && t < kStreamChunk) ? ss->buf[p][t][lane] + d0 + static_cast<uint32_t>(t + 1) * 362437u : 0u;
             }
-            if (c + kStreamBufs < n_chunks) named_bar_arrive(1 + kStreamBufs + p, 128);  // the buffer is free again
+            if (c + kStreamBufs < n_chunks) named_bar_arrive(1 + kStreamBufs + p, kHopThreads);  // the buffer is free again
+            if (q < 0) continue;  // the warp on the generator's scheduler stays out of its way
             unsigned int hit = 0;
 #pragma unroll
             for (int u = 0; u < kPer; u++) {
-                const uint32_t idx = first + 32u * (c * kStreamChunk + q + 3 * u);
+                const uint32_t idx = first + 32u * (c * kStreamChunk + q + kTesters * u);
                 num[u] = rr[u] % (idx + 1);
-                if (q + 3 * u < kStreamChunk && idx < d && num[u] < kk) hit |= 1u << u;
+                if (q + kTesters * u < kStreamChunk && idx < d && num[u] < kk) hit |= 1u << u;
             }
             if (hit) {
 #pragma unroll
                 for (int u = 0; u < kPer; u++)
-                    if (hit >> u & 1u) atomicMax(&srow[num[u]], first + 32u * (c * kStreamChunk + q + 3 * u));
+                    if (hit >> u & 1u) atomicMax(&srow[num[u]], first + 32u * (c * kStreamChunk + q + kTesters * u));
             }
         }
     }
-    named_bar_sync(1 + 2 * kStreamBufs, 128);  // every streamed draw has been evaluated: the generator may read the reservoirs
+    named_bar_sync(1 + 2 * kStreamBufs, kHopThreads);  // every streamed draw has been evaluated: the generator may read the reservoirs
 }
 
 // The rows of logical warp (b, w), executed by one physical warp whose shared-memory slice is (stage_w, slots_w, rowof_w,
@@ -379,7 +400,7 @@ __device__ __forceinline__ void warp_rows(const HopSampleArgs &a, const TileSmem
             }
         }
     }
-    if (kStream) named_bar_sync(1 + 2 * kStreamBufs, 128);  // the tester warps have evaluated every streamed draw
+    if (kStream) named_bar_sync(1 + 2 * kStreamBufs, kHopThreads);  // the tester warps have evaluated every streamed draw
     __syncwarp();
 
     // sampled rows: fetch the chosen positions; then one wait and one coalesced write-out of the whole list
@@ -424,12 +445,12 @@ __device__ __forceinline__ void warp_rows(const HopSampleArgs &a, const TileSmem
 }
 
 template <int kHub, int kMinBlocks>
-__global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kernel(const __grid_constant__ HopSampleArgs a)
+__global__ void __launch_bounds__(kHopThreads, kMinBlocks) hop_sample_kernel(const __grid_constant__ HopSampleArgs a)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ TileSmem sm;
+    __shared__ TileSmem sm[kHopTiles];
     __shared__ StreamSmem ss;
-    __shared__ uint16_t pre_sh[kSampleWarps][kRowsPerWarp];
+    __shared__ uint16_t pre_sh[kHopWarps][kRowsPerWarp];
     pdl_wait();  // everything this hop reads (frontier, CSR rows, sizes, heavy list) is the previous kernel's output
     if (a.release_early) pdl_release();
     const int64_t S = dev_size(a.S_arg, a.d_S);
@@ -438,12 +459,12 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kern
     const uint32_t kcap = a.k > 0 ? static_cast<uint32_t>(a.k) : 1u;
     const uint32_t per_warp = kRowsPerWarp * kcap;
     int64_t *stage_w = reinterpret_cast<int64_t *>(dyn_smem) + static_cast<size_t>(wp) * per_warp;
-    uint32_t *slots_w = reinterpret_cast<uint32_t *>(dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 8) +
+    uint32_t *slots_w = reinterpret_cast<uint32_t *>(dyn_smem + static_cast<size_t>(kHopWarps) * per_warp * 8) +
                         static_cast<size_t>(wp) * per_warp;
-    uint8_t *rowof_w = dyn_smem + static_cast<size_t>(kSampleWarps) * per_warp * 12 + static_cast<size_t>(wp) * per_warp;
+    uint8_t *rowof_w = dyn_smem + static_cast<size_t>(kHopWarps) * per_warp * 12 + static_cast<size_t>(wp) * per_warp;
 
     if (static_cast<int>(blockIdx.x) < a.n_front) {
-        // ---- heavy block: one listed row's logical warp; warp 0 generates, warps 1..3 test ------------------------------
+        // ---- heavy block: one listed row's logical warp; warp 0 generates, warps 1..7 test ------------------------------
         const unsigned long long n_listed = min(a.heavy[0], static_cast<unsigned long long>(kHeavyListCap));
         if (blockIdx.x >= n_listed) return;
         const int64_t r = static_cast<int64_t>(a.heavy[1 + blockIdx.x]);
@@ -456,13 +477,13 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kern
         }
         if (__syncthreads_or(dup) || r >= S) return;
         const unsigned long long t0 = g_hop_debug ? global_ns() : 0;
-        tile_prologue(a, sm, S, b, false);
+        tile_prologue(a, sm[0], S, b, false, 0);
         if (wp == 0) {
-            warp_rows<true, kHub>(a, sm, S, n_tiles, b, w, lane, stage_w, slots_w, rowof_w, pre_sh[0], &ss);
+            warp_rows<true, kHub>(a, sm[0], S, n_tiles, b, w, lane, stage_w, slots_w, rowof_w, pre_sh[0], &ss);
             if (g_hop_debug && lane == 0) {
                 unsigned int rounds = 0, big = 0;
                 for (int i = 0; i < kRowsPerWarp; i++) {
-                    const uint32_t d = sm.deg[w + kSampleWarps * i];
+                    const uint32_t d = sm[0].deg[w + kSampleWarps * i];
                     if (d > static_cast<uint32_t>(a.k)) rounds += (d - a.k + 31) >> 5;
                     big = max(big, d);
                 }
@@ -470,25 +491,72 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kern
                        (global_ns() - t0) * 1e-3);
             }
         } else
-            stream_test(a, &sm, w, wp - 1, lane, slots_w - static_cast<size_t>(wp) * per_warp, kcap, &ss);
+            stream_test(a, &sm[0], w, wp < kSampleWarps ? wp - 1 : (wp == kSampleWarps ? -1 : wp - 2), lane,
+                        slots_w - static_cast<size_t>(wp) * per_warp, kcap, &ss);
         return;
     }
 
-    // ---- regular block: one tile of 64 rows -------------------------------------------------------------------------------
-    int64_t b = static_cast<int64_t>(blockIdx.x) - a.n_front;
+    // ---- regular block: kHopTiles consecutive tiles of 64 rows, four warps each ---------------------------------------------
+    int64_t blk = static_cast<int64_t>(blockIdx.x) - a.n_front;
     if (a.ticket) {  // grids larger than the device holds at once: tiles in dispatch order, so look-back never waits on a
-        if (threadIdx.x == 0) sm.tile = static_cast<int>(atomicAdd(a.ticket, 1ull));  // tile whose block has not started
+        if (threadIdx.x == 0) sm[0].tile = static_cast<int>(atomicAdd(a.ticket, 1ull));  // tile whose block has not started
         __syncthreads();
-        b = sm.tile;
+        blk = sm[0].tile;
+        __syncthreads();
+    }
+    if (blk * kHopTiles >= n_tiles) return;
+    const int ts = wp / kSampleWarps;  // this warp's tile slot
+    const int64_t b = blk * kHopTiles + ts;
+    // both tiles' CSR rows are loaded at once (threads 0..63 / 128..191), scanned by warps 0 / 4
+    {
+        const int t = static_cast<int>(threadIdx.x) - ts * (kSampleWarps * 32);
+        if (t < kSampleTile) {
+            const int64_t r = b * kSampleTile + t;
+            int64_t start = 0, deg = 0;
+            if (r < S) {
+                if (a.cached_deg) {
+                    start = a.cached_start[r];
+                    deg = a.cached_deg[r];
+                } else {
+                    const int64_t node = a.seeds[r];
+                    if (node >= 0 && node < a.n_nodes) {
+                        start = a.indptr[node];
+                        deg = a.indptr[node + 1] - start;
+                        if (a.node_map)  // hop 0: the seeds enter the node map
+                            atomicMin(&a.node_map[node], map_word(a.epoch_hi, kMapCand + static_cast<unsigned int>(r)));
+                    } else if (a.node_map) {
+                        *a.d_err = 1;
+                    }
+                }
+            }
+            sm[ts].start[t] = start;
+            sm[ts].deg[t] = static_cast<uint32_t>(min(deg, static_cast<int64_t>(0xffffffffu)));
+        }
+        __syncthreads();
+        if (t < 32) {
+            const uint32_t kk = static_cast<uint32_t>(a.k);
+            const uint32_t c0 = min(sm[ts].deg[2 * t], kk), c1 = min(sm[ts].deg[2 * t + 1], kk);
+            uint32_t incl = c0 + c1;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, off);
+                if (t >= off) incl += u;
+            }
+            sm[ts].excl[2 * t] = incl - c0 - c1;
+            sm[ts].excl[2 * t + 1] = incl - c1;
+            if (t == 31) {
+                sm[ts].total = incl;
+                if (!a.tile_base && b < n_tiles)  // hop 0: the tile's count is public from now on (look-back at write-out)
+                    st_volatile_u64(a.desc + b, (b == 0 ? kFlagPrefix : kFlagAgg) | (static_cast<unsigned long long>(incl) & kValueMask));
+            }
+        }
+        __syncthreads();
     }
     if (b >= n_tiles) return;
-    tile_prologue(a, sm, S, b, true);
-    if (threadIdx.x == 0 && !a.tile_base)  // the tile's count is public from now on; its inclusive prefix follows at write-out
-        st_volatile_u64(a.desc + b, (b == 0 ? kFlagPrefix : kFlagAgg) | (static_cast<unsigned long long>(sm.total) & kValueMask));
-    const int w = wp;
+    const int w = wp % kSampleWarps;
     if (a.n_front > 0) {
         // does a heavy block serve this warp?  (only warps owning a listed-size row need to look)
-        const bool big = lane < kRowsPerWarp && sm.deg[w + kSampleWarps * lane] > kHeavyDeg;
+        const bool big = lane < kRowsPerWarp && sm[ts].deg[w + kSampleWarps * lane] > kHeavyDeg;
         if (__any_sync(0xffffffffu, big)) {
             const unsigned int n_listed = static_cast<unsigned int>(min(a.heavy[0], static_cast<unsigned long long>(kHeavyListCap)));
             bool found = false;
@@ -499,7 +567,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32, kMinBlocks) hop_sample_kern
             if (__any_sync(0xffffffffu, found)) return;
         }
     }
-    warp_rows<false, kHub>(a, sm, S, n_tiles, b, w, lane, stage_w, slots_w, rowof_w, pre_sh[wp], nullptr);
+    warp_rows<false, kHub>(a, sm[ts], S, n_tiles, b, w, lane, stage_w, slots_w, rowof_w, pre_sh[wp], nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -2062,15 +2062,16 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
     QV_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * sizeof(unsigned long long), st));
 
     int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start + bn[n_hops];
-    // 18 KB of static + a few KB of dynamic shared memory per 128-thread block: with the default carve-out the SM fits 4 such
-    // blocks (ncu: occupancy limit "shared mem 4" against "registers 8"); ask for the largest shared-memory carve-out instead
-    static const bool carve = [] {
-        cudaFuncSetAttribute(hop_sample_kernel<4, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaGetLastError();
-        return true;
-    }();
-    (void)carve;
-    static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 8>), kSampleWarps * 32, 0);
+    // 35 KB of static + 4-53 KB of dynamic shared memory per 256-thread block: ask for the largest shared-memory carve-out
+    // (with the default one ncu showed the shared-memory occupancy limit at half the register limit)
+    static unsigned long long attr_set = 0;  // per device (function attributes belong to the device's copy of the kernel)
+    if (s->device < 0 || s->device >= 64 || !(attr_set >> s->device & 1ull)) {
+        cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // 35 KB static (tiles + ring) + up to 53 KB dynamic at k = 32 exceeds the 48 KB a kernel gets without opting in
+        QV_CUDA(cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        if (s->device >= 0 && s->device < 64) attr_set |= 1ull << s->device;
+    }
+    static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 4>), kHopThreads, 0);
     for (int h = 0; h < n_hops; h++) {
         int64_t *m = s->d_meta + kMetaStride * h;
         unsigned long long *hop = ctl + kCtlHeader + stride * h;
@@ -2107,12 +2108,13 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
         }
         a.n_front = (h == 0 || s->max_degree <= kHeavyDeg) ? 0 : kHeavyListCap;
         const int64_t tiles = (bn[h] + kSampleTile - 1) / kSampleTile;
-        const size_t smem = static_cast<size_t>(kSampleWarps) * kRowsPerWarp * std::max(k, 1) * 13;
-        a.ticket = (h == 0 && tiles > int64_t(sample_per_sm) * s->n_sm) ? hop : nullptr;  // only hop 0 looks back
+        const int64_t blocks = (tiles + kHopTiles - 1) / kHopTiles;
+        const size_t smem = static_cast<size_t>(kHopWarps) * kRowsPerWarp * std::max(k, 1) * 13;
+        a.ticket = (h == 0 && blocks > int64_t(sample_per_sm) * s->n_sm) ? hop : nullptr;  // only hop 0 looks back
         // a grid of at most ~3 blocks per SM leaves registers and threads for the reindex kernel's two 512-thread blocks
         static const bool early_off = getenv("QV_HOP_EARLY") && getenv("QV_HOP_EARLY")[0] == '0';
-        a.release_early = (!early_off && tiles + a.n_front <= int64_t(3) * s->n_sm) ? 1 : 0;
-        QV_CUDA(launch_chained(hop_sample_kernel<4, 8>, static_cast<unsigned>(tiles + a.n_front), kSampleWarps * 32, smem, st, a));
+        a.release_early = (!early_off && blocks + a.n_front <= int64_t(3) * s->n_sm / 2) ? 1 : 0;
+        QV_CUDA(launch_chained(hop_sample_kernel<4, 4>, static_cast<unsigned>(blocks + a.n_front), kHopThreads, smem, st, a));
         QV_CHECK_LAUNCH("hop_sample_kernel");
 
         HopReindexArgs r;
