@@ -575,3 +575,25 @@ def test_khop_against_committed_golden_vectors(golden_dir):
             assert n_id.cpu().tolist() == c["n_id"] and bs == len(c["seeds"]), (c["name"], fused)
             for adj, want in zip(adjs, c["adjs"]):
                 assert adj.edge_index.cpu().tolist() == want["edge_index"] and adj.size.tolist() == want["size"]
+
+
+def test_pinned_host_seeds_are_read_in_place(oracle):
+    """Seeds in pinned host memory go to the fused call as they are (hop 0's kernels read them over PCIe): same results as
+    device seeds and as unpinned host seeds (which are copied), through sample() and sample_and_gather()."""
+    import quiver
+    indptr, indices = powerlaw_csr(20000, 25.0, seed=10)
+    topo = quiver.CSRTopo(indptr=indptr, indices=indices)
+    sampler = quiver.pyg.GraphSageSampler(topo, [15, 10, 5], device=0, mode="GPU")
+    x = torch.from_numpy(np.random.default_rng(0).integers(0, 10, (20000, 16)).astype(np.float32))
+    feature = quiver.Feature(rank=0, device_list=[0], device_cache_size="64M", csr_topo=topo)
+    feature.from_cpu_tensor(x)
+    seeds = torch.from_numpy(np.random.default_rng(3).permutation(20000)[:700])
+    want_nid, _, want_adjs = sampler.sample(seeds.cuda())
+    o_nid, _, _ = oracle.khop(indptr, indices, seeds.numpy(), [15, 10, 5])
+    assert torch.equal(want_nid.cpu(), torch.from_numpy(o_nid))
+    for s in (seeds.pin_memory(), seeds):
+        n_id, bs, adjs = sampler.sample(s)
+        assert bs == 700 and torch.equal(n_id, want_nid)
+        assert all(torch.equal(a.edge_index, b.edge_index) for a, b in zip(adjs, want_adjs))
+        n_id2, _, adjs2, rows = sampler.sample_and_gather(s, feature)
+        assert torch.equal(n_id2, want_nid) and torch.equal(rows.cpu(), x[want_nid.cpu()])

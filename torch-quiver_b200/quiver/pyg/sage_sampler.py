@@ -105,6 +105,13 @@ class GraphSageSampler:
         self.device = torch.cuda.current_device()
         self.quiver = self._build(self.device)
 
+    def _device_visible(self, nodes):
+        """Seeds as the fused call takes them: pinned host memory is read in place by the first hop's kernels (no staging
+        copy, no allocation); anything else is copied to the device."""
+        if not nodes.is_cuda and nodes.dtype == torch.int64 and nodes.is_pinned() and nodes.is_contiguous():
+            return nodes
+        return nodes.to(self.device, non_blocking=True)
+
     def sample_layer(self, batch, size):
         self.lazy_init_quiver()
         if not isinstance(batch, torch.Tensor):
@@ -128,7 +135,7 @@ class GraphSageSampler:
                 if self.overlap:
                     n_id, hops = self._sample_khop_overlapped(input_nodes)
                 else:
-                    n_id, hops = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes,
+                    n_id, hops = self.quiver.sample_khop(self._device_visible(input_nodes), self.sizes,
                                                          with_eid=self.return_eid)
             except qv.Unsupported:
                 pass
@@ -174,7 +181,7 @@ class GraphSageSampler:
         if (store is not None and self.fused and not self.overlap and batch_size > 0 and all(s >= 0 for s in self.sizes)
                 and torch.cuda.current_device() == self.device):
             try:
-                n_id, hops, x = self.quiver.sample_khop(input_nodes.to(self.device, non_blocking=True), self.sizes,
+                n_id, hops, x = self.quiver.sample_khop(self._device_visible(input_nodes), self.sizes,
                                                         gather=(store, order), with_eid=self.return_eid)
             except qv.Unsupported:
                 pass

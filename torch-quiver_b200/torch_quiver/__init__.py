@@ -216,7 +216,14 @@ class Quiver:
         calls).  The whole block stays alive while the caller holds x; `x = x.clone()` releases it.
 
         with_eid=True: every hop tuple gains a 4th element, the e_id of its edges (CSR position or user edge id)."""
-        v = _check_long_cuda(seeds, "seeds", self.device)
+        # seeds: a CUDA tensor, or a PINNED host tensor -- pinned memory is device-visible at the same address under unified
+        # addressing, so the kernels of hop 0 read the seeds straight over PCIe (8 KB) and the call needs no staging copy
+        if isinstance(seeds, torch.Tensor) and not seeds.is_cuda and seeds.dtype == torch.int64 and seeds.is_pinned() \
+                and seeds.is_contiguous():
+            v = seeds
+        else:
+            v = _check_long_cuda(seeds, "seeds", self.device)
+        out_dev = torch.device("cuda", self.device)
         n_hops = len(sizes)
         S = v.numel()
         key = (S, tuple(int(x) for x in sizes))
@@ -244,7 +251,7 @@ class Quiver:
                 self._khop_plans.clear()
             self._khop_plans[key] = plan
         sz, n_id_cap, offs, total, buf_ptrs, out_nodes, out_edges, eoffs, etotal, eid_ptrs = plan
-        arena = torch.empty(etotal if with_eid else total, dtype=torch.int64, device=v.device)
+        arena = torch.empty(etotal if with_eid else total, dtype=torch.int64, device=out_dev)
         base = arena.data_ptr()
         for h in range(n_hops):
             buf_ptrs[h] = base + 8 * offs[h]
@@ -268,7 +275,7 @@ class Quiver:
             order_ptr = c_void_p(0)
             if feature_order is not None:
                 order_ptr = _ptr(_check_long_cuda(feature_order, "feature_order", self.device))
-            x = torch.empty([x_rows] + row_shape, dtype=dtype, device=v.device)
+            x = torch.empty([x_rows] + row_shape, dtype=dtype, device=out_dev)
             check(lib.qv_khop_gather(self._handle, _ptr(v), S, sz, n_hops, int(self.rand_seed), c_void_p(base), buf_ptrs,
                                      eid_arg, byref(table), order_ptr, row_bytes, _ptr(x), x_rows,
                                      int(store.gather_variant), out_nodes, out_edges, _stream(self.device)))
