@@ -538,13 +538,6 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     # ---- setup (untimed) ---------------------------------------------------------------------------------------------
     t_setup = time.perf_counter()
-    pre_store = None
-    if os.environ.get("QV_BENCH_ALLOC_FIRST"):  # experiment: feature shards allocated BEFORE anything else touched the GPU
-        from quiver.shard_tensor import build_tiered_inplace
-        if world > 1:
-            quiver.init_p2p(list(range(world)))
-        pre_store = build_tiered_inplace(dev.index, n, [dim], torch.float32, lambda v, lo, hi: None,
-                                         hot_rows=int(n * args.hot_frac) if world > 1 else 0, cold_rows=0, broadcast_hot=False)
     indptr, indices = make_graph(dev, cfg)
     n_edges = indices.numel()
     torch.cuda.empty_cache()
@@ -558,13 +551,8 @@ def run_ours(args, cfg, rank, world, local_rank):
     sampler.inputs_ready = True  # the device-resident seed batches below are materialised before the timed region
     if world > 1:
         quiver.init_p2p(list(range(world)))
-    if pre_store is not None:
-        feature = quiver.Feature.from_tiered_store(dev.index, pre_store[0], None)
-        fuse_target, feature_order, placement, info, x_cpu = feature, None, "experiment: uninitialised shards allocated first", \
-            pre_store[1], None
-    else:
-        feature, fuse_target, feature_order, placement, info, x_cpu = build_feature(args, cfg, dev, rank, world, indptr,
-                                                                                     indices if not args.uva else None, sampler)
+    feature, fuse_target, feature_order, placement, info, x_cpu = build_feature(args, cfg, dev, rank, world, indptr,
+                                                                                 indices if not args.uva else None, sampler)
     feature._my_store().shard_tensor.gather_variant = args.gather_variant
     n_rep = max(1, args.repeats)
     n_batches = args.warmup + n_rep * args.steps
@@ -649,8 +637,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     for j in (0, args.steps - 1):
         got = feature[nid_keep[j]]
         want = feat_formula(nid_keep[j], dim, dev)
-        assert pre_store is not None or torch.equal(got, want), \
-            f"rank {rank}: gathered rows differ from the feature formula (batch {j})"
+        assert torch.equal(got, want), f"rank {rank}: gathered rows differ from the feature formula (batch {j})"
         parity_rows += got.shape[0]
         del got, want
     tier_rows = None
@@ -737,10 +724,6 @@ def run_ours(args, cfg, rank, world, local_rank):
     # (outputs are pre-allocated and the C-ABI call is issued directly so the host never starves the queue: the interval
     #  between the two events is back-to-back executions of the gather kernel and nothing else)
     st_raw = feature._my_store().shard_tensor
-    if os.environ.get("QV_BENCH_RANDIDX"):  # experiment: uniform random ids instead of the sampled frontiers
-        nid_keep = [torch.randint(0, n, (x.numel(), ), device=dev) for x in nid_keep]
-    if os.environ.get("QV_BENCH_SORTIDX"):  # experiment: the same frontiers, sorted
-        nid_keep = [torch.sort(x)[0] for x in nid_keep]
     max_rows = max(x.numel() for x in nid_keep)
     outs = [torch.empty(max_rows, dim, device=dev) for _ in range(2)]
     for j, x in enumerate(nid_keep[:2]):
