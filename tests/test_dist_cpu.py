@@ -80,3 +80,38 @@ def test_build_from_ranks_world2_gloo():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
     assert results.tolist() == [1, 1]
+
+
+def _tier_worker(rank, world, port, results):
+    sys.path[:0] = [ROOT, PKG]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quiver.shard_tensor import tier_ranges
+    n, hot, cold = 1003, 200, 101
+    mine = tier_ranges(n, hot, cold, world, rank)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    ok = all(e["hot"] == (0, hot) and e["cold"] == (n - cold, n) and e["striped"] == (hot, n - cold) for e in everyone)
+    stripes = [e["stripe"] for e in everyone]
+    ok &= stripes[0][0] == hot and stripes[-1][1] == n - cold
+    ok &= all(stripes[r][1] == stripes[r + 1][0] for r in range(world - 1))  # the ranks' blocks tile [hot, n - cold) in order
+    ok &= mine == everyone[rank]
+    results[rank] = 1 if ok else 0
+    dist.destroy_process_group()
+
+
+def test_tiered_layout_ranges_world2_gloo():
+    """build_tiered_inplace's layout arithmetic (hot prefix replicated | one stripe per rank | cold host suffix) agreed
+    on by two ranks over a real gloo rendezvous; plus the single-rank and error cases."""
+    from quiver.shard_tensor import tier_ranges
+    world = 2
+    results = torch.zeros(world, dtype=torch.int32).share_memory_()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_tier_worker, args=(world, port, results), nprocs=world, join=True)
+    assert results.tolist() == [1, 1]
+    one = tier_ranges(1000, 300, 100, 1, 0)  # a single GPU has no replicated tier: everything that is not cold is its shard
+    assert one["hot"] == (0, 0) and one["stripe"] == (0, 900) and one["cold"] == (900, 1000)
+    eight = [tier_ranges(100_000_000, 40_000_000, 0, 8, r)["stripe"] for r in range(8)]
+    assert eight[0] == (40_000_000, 47_500_000) and eight[-1][1] == 100_000_000
+    with pytest.raises(ValueError):
+        tier_ranges(10, 8, 5, 2, 0)

@@ -217,6 +217,21 @@ def _fill_chunked(view, lo, fill, chunk_elems=1 << 26):
         fill(view[a:b], lo + a, lo + b)
 
 
+def tier_ranges(n_rows, hot_rows, cold_rows, world, rank):
+    """Storage-row ranges of the tiered layout as seen from `rank`: {"hot": replicated prefix, "stripe": this rank's block,
+    "striped": all ranks' blocks together, "cold": host suffix}.  Pure arithmetic (tested on CPU under gloo): the stripes of
+    ranks 0..world-1 tile [H, n - C) in order, the last one takes the remainder; a single rank has no hot tier."""
+    H, C = int(hot_rows), int(cold_rows)
+    if not (0 <= H and 0 <= C and H + C <= n_rows):
+        raise ValueError(f"hot ({H}) + cold ({C}) rows exceed the table ({n_rows})")
+    if world == 1:
+        H = 0
+    per = (n_rows - H - C) // world
+    lo = H + rank * per
+    hi = H + (rank + 1) * per if rank < world - 1 else n_rows - C
+    return {"hot": (0, H), "stripe": (lo, hi), "striped": (H, n_rows - C), "cold": (n_rows - C, n_rows), "world": world}
+
+
 def build_tiered_inplace(device, n_rows, row_shape, dtype, fill, hot_rows=0, cold_rows=0, group=None,
                          broadcast_hot=True, shm_tag=None):
     """Create an [n_rows, *row_shape] table over the ranks of `group` (None / uninitialised = this process alone).
@@ -234,14 +249,8 @@ def build_tiered_inplace(device, n_rows, row_shape, dtype, fill, hot_rows=0, col
     use_dist = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if use_dist else 0
     world = dist.get_world_size(group) if use_dist else 1
-    H, C = int(hot_rows), int(cold_rows)
-    assert 0 <= H and 0 <= C and H + C <= n_rows
-    if world == 1:
-        H = 0  # a single GPU holds everything that is not cold: one shard
-    mid = n_rows - H - C
-    per = mid // world
-    lo = H + rank * per
-    hi = H + (rank + 1) * per if rank < world - 1 else n_rows - C
+    info = tier_ranges(n_rows, hot_rows, cold_rows, world, rank)
+    (_, H), (lo, hi), C = info["hot"], info["stripe"], info["cold"][1] - info["cold"][0]
     st = ShardTensor(device, ShardTensorConfig({}))
     raw = st.shard_tensor
     with torch.cuda.device(device):
@@ -306,5 +315,4 @@ def build_tiered_inplace(device, n_rows, row_shape, dtype, fill, hot_rows=0, col
         raw.append(cold, -1)
     if use_dist:
         dist.barrier(group)  # nobody gathers before every peer mapping exists and every tier is filled
-    info = {"hot": (0, H), "stripe": (lo, hi), "striped": (H, n_rows - C), "cold": (n_rows - C, n_rows), "world": world}
     return st, info
