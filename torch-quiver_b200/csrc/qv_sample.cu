@@ -79,6 +79,45 @@ cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// A kernel that synchronises its whole grid (hop_reindex_kernel).  Its grid is bounded by the occupancy, which is enough while
+// it is the only such grid on the device; two of them on two streams (two samplers of one process sampling concurrently)
+// could each hold half the SMs and spin on the other half forever.  A COOPERATIVE launch makes the driver schedule the
+// grid only when every block can be resident at once -- at ~4 us per launch (measured: 3 launches per step, 198-230 ->
+// 213-237 us per north-star sample), so it is used when it is needed: `coop` = a second sampler exists on this device
+// (or QV_COOP=1; QV_COOP=0 never).  Several PROCESSES sharing a GPU under MPS must set QV_COOP=1.
+std::atomic<int> g_live_samplers[64];
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_grid_sync(bool coop, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args &&...args)
+{
+    static const int forced = getenv("QV_COOP") ? atoi(getenv("QV_COOP")) : -1;
+    static int mode = 2;  // 2: cooperative + programmatic dependent launch, 1: cooperative only
+    if (forced == 0 || (forced < 0 && !coop)) return launch_chained(kernel, grid, block, smem, st, std::forward<Args>(args)...);
+    static const bool pdl = !(getenv("QV_PDL") && getenv("QV_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    if (mode == 2) {
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+        if (e == cudaSuccess) return e;
+        cudaGetLastError();
+        mode = 1;  // this driver does not combine the two attributes: cooperative launches without the early hand-over
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Single-pass chained scan (decoupled look-back).  Tile descriptors: bits 63..62 = flag, 61..0 = value.
 // Tiles take their index from an atomic ticket so a tile only ever waits on tiles that are already running.
@@ -1413,6 +1452,7 @@ struct qv_sampler {
     unsigned int recip_n = 0;
     int64_t max_degree = 0;
     const int64_t *edge_ids = nullptr;  // optional user edge ids per CSR position (qv_sampler_set_edge_ids); borrowed
+    bool counted = false;               // this object is in g_live_samplers (see launch_grid_sync)
 };
 
 namespace
@@ -1683,6 +1723,8 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
         const int hop_dbg = getenv("QV_HOP_DEBUG") ? atoi(getenv("QV_HOP_DEBUG")) : 0;
         cudaMemcpyToSymbol(g_hop_debug, &hop_dbg, sizeof hop_dbg);
     }
+    if (device >= 0 && device < 64) g_live_samplers[device].fetch_add(1);
+    s->counted = true;
     *out = s;
     return QV_OK;
 }
@@ -1690,6 +1732,7 @@ int qv_sampler_create(int device, const int64_t *indptr, int64_t n_nodes, const 
 int qv_sampler_destroy(qv_sampler *s)
 {
     if (!s) return QV_OK;
+    if (s->counted && s->device >= 0 && s->device < 64) g_live_samplers[s->device].fetch_sub(1);
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();
     s->scan.release();
@@ -2146,12 +2189,13 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
             r.k_next = sizes[h + 1];
         }
         const ReindexPlan plan = plan_reindex(s, be[h] + (h == 0 ? S : 0));
+        const bool coop = s->device >= 0 && s->device < 64 && g_live_samplers[s->device].load() > 1;
         switch (plan.items) {
-        case 1: QV_CUDA(launch_chained(hop_reindex_kernel<1>, plan.grid, kReindexThreads, 0, st, r)); break;
-        case 2: QV_CUDA(launch_chained(hop_reindex_kernel<2>, plan.grid, kReindexThreads, 0, st, r)); break;
-        case 4: QV_CUDA(launch_chained(hop_reindex_kernel<4>, plan.grid, kReindexThreads, 0, st, r)); break;
-        case 8: QV_CUDA(launch_chained(hop_reindex_kernel<8>, plan.grid, kReindexThreads, 0, st, r)); break;
-        default: QV_CUDA(launch_chained(hop_reindex_kernel<16>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 1: QV_CUDA(launch_grid_sync(coop, hop_reindex_kernel<1>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 2: QV_CUDA(launch_grid_sync(coop, hop_reindex_kernel<2>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 4: QV_CUDA(launch_grid_sync(coop, hop_reindex_kernel<4>, plan.grid, kReindexThreads, 0, st, r)); break;
+        case 8: QV_CUDA(launch_grid_sync(coop, hop_reindex_kernel<8>, plan.grid, kReindexThreads, 0, st, r)); break;
+        default: QV_CUDA(launch_grid_sync(coop, hop_reindex_kernel<16>, plan.grid, kReindexThreads, 0, st, r)); break;
         }
         QV_CHECK_LAUNCH("hop_reindex_kernel");
     }
