@@ -395,7 +395,7 @@ def run_reference(args, cfg, rank, world):
 # ----------------------------------------------------------------------------------------------------------------------
 # the reference's CUDA kernels on the same GPU (oracle/_ref/torch_quiver_ref_cuda*.so, N=1 only)
 # ----------------------------------------------------------------------------------------------------------------------
-def ref_gpu_baseline(cfg, dev, indptr, indices, batches_dev, nid_list, n_batches=3):
+def ref_gpu_baseline(cfg, dev, indptr, indices, batches_dev, nid_list, n_batches=5):
     """SURVEY 2.2's bar: the reference's own kernels recompiled for sm_100a, same GPU, same batches.  Sampler = the hop loop
     of sage_sampler.py:118-147 over Quiver.sample_neighbor / reindex_single; gather = ShardTensor.__getitem__ over a
     bounded HBM table (ids folded modulo its rows: the reference can only create shards from CPU tensors)."""
@@ -415,12 +415,18 @@ def ref_gpu_baseline(cfg, dev, indptr, indices, batches_dev, nid_list, n_batches
 
     sample(batches_dev[0])
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    edges = 0
+    edges, per_batch = 0, []
     for b in batches_dev[1:1 + n_batches]:
-        edges += sample(b)[1]
-    torch.cuda.synchronize()
-    t_sample = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        e = sample(b)[1]
+        torch.cuda.synchronize()
+        per_batch.append((time.perf_counter() - t0, e))
+        edges += e
+    # the reference allocates ~10 thrust vectors per hop with cudaMalloc/cudaFree; next to a 100 GB table single calls take
+    # 10-30 ms now and then, so the figure is the MEDIAN batch (min / max alongside)
+    per_batch.sort(key=lambda t: t[0] / max(t[1], 1))
+    t_med, e_med = per_batch[len(per_batch) // 2]
+    t_sample = t_med * n_batches * (edges / max(e_med * n_batches, 1))
     dim = cfg["feat_dim"]
     rows = int(min(cfg["n_nodes"], (4 << 30) // (dim * 4)))
     x = torch.empty(rows, dim).fill_(0.25)
@@ -444,8 +450,9 @@ def ref_gpu_baseline(cfg, dev, indptr, indices, batches_dev, nid_list, n_batches
             "feature_gather_GBps": n_rows * dim * 4 / t_gather / 1e9, "gather_ms_per_step": t_gather / n_batches * 1e3,
             "edges_per_s_step": edges / (t_sample + t_gather),
             "gather_table": f"{rows} rows in HBM" + ("" if rows >= cfg["n_nodes"] else " (ids folded modulo rows)"),
-            "batches": n_batches, "timing": "sampler: wall clock around synchronising calls (the reference blocks on the "
-                                            "host several times per hop); gather: CUDA events"}
+            "batches": n_batches, "seps_sampler_min_max": [min(e / t for t, e in per_batch), max(e / t for t, e in per_batch)],
+            "timing": "sampler: wall clock around synchronising calls (the reference blocks on the host several times per "
+                      "hop and allocates with cudaMalloc per call), median batch; gather: CUDA events"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -631,3 +631,22 @@ def test_two_samplers_on_one_device_sample_concurrently(oracle):
         th.join(timeout=150)
     assert not any(th.is_alive() for th in threads), "the two samplers dead-locked"
     assert not errors, errors
+
+
+@pytest.mark.parametrize("rand_seed", [1, 2**33 + 5])
+def test_fused_khop_with_another_generator_seed(oracle, rand_seed):
+    """rand_seed != 0 (the reference hard-codes 0): the per-launch generator states depend on each hop's row count, which
+    only the device knows in the fused call -- same ids as the oracle's hop loop with that seed, heavy rows included."""
+    import torch_quiver as qv
+    indptr, indices = powerlaw_csr(30000, 40.0, seed=15, alpha=1.4)
+    assert np.diff(indptr).max() > 3072  # above the heavy-list threshold: streamed rows too
+    q = qv.device_quiver_from_csr_array(torch.from_numpy(indptr), torch.from_numpy(indices), None, 0, True)
+    q.rand_seed = rand_seed
+    hubs = np.argsort(-np.diff(indptr))[:5]
+    rest = np.random.default_rng(9).permutation(30000)[:600]
+    seeds = np.concatenate([hubs, rest[~np.isin(rest, hubs)]])
+    n_id, hops = q.sample_khop(_dev(seeds), [10, 5, 3])
+    o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, [10, 5, 3], rand_seed=rand_seed)
+    assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
+    for (ei, _, _), (o_ei, _) in zip(hops, o_adjs[::-1]):
+        assert torch.equal(ei.cpu(), torch.from_numpy(o_ei))
