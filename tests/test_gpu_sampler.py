@@ -650,3 +650,31 @@ def test_fused_khop_with_another_generator_seed(oracle, rand_seed):
     assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid))
     for (ei, _, _), (o_ei, _) in zip(hops, o_adjs[::-1]):
         assert torch.equal(ei.cpu(), torch.from_numpy(o_ei))
+
+
+def test_heavy_list_grows_past_its_initial_cap(oracle):
+    """Fused k-hop, hop_sample_kernel: rows above 3072 neighbours are served by front-of-grid heavy blocks, 256 of them on a
+    sampler's first call; a call that sees more (R-MAT frontiers do) leaves the overflow on the regular schedule and the
+    sampler widens the front for the next call (up to 2048).  700 such rows, several per logical warp, heavy rows also
+    first met on hop 1: ids, edge_index and e_id bit-exact with the oracle on the overflowing call and on the grown ones."""
+    rng = np.random.default_rng(77)
+    n = 40000
+    n_heavy = 700
+    deg = rng.integers(0, 10, n)
+    deg[:n_heavy] = rng.integers(3100, 5000, n_heavy)
+    indptr = np.zeros(n + 1, np.int64)
+    np.cumsum(deg, out=indptr[1:])
+    indices = rng.integers(0, n, int(indptr[-1])).astype(np.int64)
+    indices[rng.random(indices.shape[0]) < 0.3] = rng.integers(0, n_heavy, 1)[0]  # one heavy hub met again and again
+    light = indptr[n_heavy]
+    indices[light::5] = rng.integers(0, n_heavy, indices[light::5].shape[0])  # light rows lead to heavy ones on hop 1
+    q = _quiver(indptr, indices)
+    sizes = [6, 4, 3]
+    for it in range(3):
+        seeds = np.concatenate([rng.permutation(n_heavy)[:300], n_heavy + rng.permutation(n - n_heavy)[:500]]).astype(np.int64)
+        n_id, hops = q.sample_khop(_dev(seeds), sizes, with_eid=True)
+        o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, sizes, with_eid=True)
+        assert torch.equal(n_id.cpu(), torch.from_numpy(o_nid)), it
+        for hop, (o_ei, _, o_pos) in zip(hops, o_adjs[::-1]):
+            assert torch.equal(hop[0].cpu(), torch.from_numpy(o_ei)), it
+            assert torch.equal(hop[3].cpu(), torch.from_numpy(o_pos)), it

@@ -15,35 +15,38 @@
 // kernels that do a few hundred ns of work behind a launch + dependency latency.
 //
 // Heavy rows.  Parity pins lane l of logical warp (b, w) to ONE XORWOW stream serving that warp's rows in order, so the
-// draws of a long row are a dependent chain.  What is NOT pinned is who evaluates them: in a "heavy block" warp 0 only
-// advances the 32 generators (7 instructions per draw, an 8-cycle dependency) and streams the raw outputs through a
-// double-buffered shared-memory ring; warps 1-3 add the Weyl term, look up the fastmod reciprocal, test `r mod m < k` and
-// atomicMax the reservoir.  The chain then runs at ~9 cycles per draw instead of ~30 (one warp can issue one instruction
-// per cycle; the test is ~3x the generator's instruction count).  The warps that own such rows are known before the hop
-// starts: every node's degree is recorded when it joins the frontier (hop_reindex_kernel appends rows above kHeavyDeg to
-// a per-call list), so heavy blocks sit at the FRONT of the grid and start at time zero (longest-first), and the row's
-// regular slot retires when it finds itself listed.
+// draws of a long row are a dependent chain.  What is NOT pinned is who evaluates them: in a "heavy block" (256 threads)
+// warp 0 only advances the 32 generators (7 instructions per draw on a ~15-cycle dependency, profiles/micro/xorwow_chain.cu)
+// and streams the raw outputs through a kStreamBufs-deep shared-memory ring guarded by named barriers; six tester warps
+// (1-3, 5-7) add the Weyl term, evaluate `r mod m < k` (ten independent `%` per batch: the divides pipeline, a reciprocal
+// table's cold loads did not) and atomicMax the reservoir; warp 4, which shares warp 0's scheduler, only joins the
+// barriers.  Measured: 23.6 cycles per draw in the kernel against 30-100 before (profiles/r2_hop_sample_ns_full.txt).  The
+// warps that own such rows are known before the hop starts: every node's degree is recorded when it joins the frontier
+// (hop_reindex_kernel appends rows above kHeavyDeg to a per-call list), so heavy blocks sit at the FRONT of the grid and
+// start at time zero (longest-first), and the row's regular slot retires when it finds itself listed.
 #pragma once
 
 constexpr int kHeavyDeg = 3072;     // rows with more neighbours join the call's heavy list (>= 96 draws per lane)
-constexpr int kHeavyListCap = 256;  // listed rows = heavy blocks at the front of every later hop's sampling grid
+constexpr int kHeavyListMax = 2048;  // capacity of the call's heavy list
+constexpr int kHeavyFrontInit = 256;  // listed rows = heavy blocks at the front of every later hop's sampling grid: a sampler
+                                      // starts here and grows towards kHeavyListMax when a call lists more (R-MAT graphs do)
 constexpr int kStreamMin = 64;      // draws per lane from which a row of a heavy block is streamed to the tester warps
 constexpr int kStreamChunk = 60;    // draws per lane per ring buffer (a multiple of kGenUnroll)
 constexpr int kGenUnroll = 10;      // generator steps per loop iteration (a multiple of 5 keeps the state rotation free of moves)
 constexpr int kHopTiles = 2;        // 64-row tiles per regular block
-constexpr int kHopWarps = kHopTiles * kSampleWarps;  // 8 warps: a heavy block is 1 generator warp + 7 tester warps
+constexpr int kHopWarps = kHopTiles * kSampleWarps;  // 8 warps: a heavy block is 1 generator warp + 6 testers + 1 idle
 constexpr int kHopThreads = kHopWarps * 32;
 constexpr int kTesters = kHopWarps - 2;  // warp 4 shares the generator's scheduler: it only joins the barriers (see stream_test)
 constexpr int kStreamBufs = 4;      // ring depth (named barriers 1..4 = full, 5..8 = empty, 9 = all draws evaluated; all of kHopThreads)
 
 // ---- control words of one fused k-hop call (zeroed by one memset) ----------------------------------------------------
-//   ctl[0]                 number of heavy rows listed so far (may exceed the cap: entries beyond it are dropped)
-//   ctl[1 .. 1+cap)        row index (= local id, stable across hops) of each listed row
+//   ctl[0]                 number of heavy rows listed so far (may exceed the call's cap n_front: entries beyond it are dropped)
+//   ctl[1 .. 1+max)        row index (= local id, stable across hops) of each listed row
 //   per hop h, at ctl + kCtlHeader + h * stride:
 //     [0] tile ticket of the sampling kernel   [1] grid-barrier counter of the reindex kernel
 //     [2 .. 2+2*kReindexMaxBlocks)  per-block first-occurrence counts, then per-block next-hop entry counts
 //     [2+2*kReindexMaxBlocks ..)    hop 0 only: sampling tile descriptors
-constexpr int kCtlHeader = 1 + kHeavyListCap + 7;  // 264 words: keeps the per-hop regions 64-byte aligned
+constexpr int kCtlHeader = 1 + kHeavyListMax + 7;  // 2056 words: keeps the per-hop regions 64-byte aligned
 constexpr int kReindexMaxBlocks = 512;
 constexpr int kHopCtlFixed = 2 + 2 * kReindexMaxBlocks;
 
@@ -55,12 +58,17 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
+// bar.sync / bar.arrive are the .aligned forms: every thread of the warp must execute them together, and independent
+// thread scheduling does not promise that a warp has reconverged after the divergent reservoir updates in front of them
+// (compute-sanitizer synccheck flagged exactly that) -- hence the __syncwarp() first.
 __device__ __forceinline__ void named_bar_sync(int id, int count)
 {
+    __syncwarp();
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int count)
 {
+    __syncwarp();
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
@@ -87,7 +95,7 @@ struct HopSampleArgs {
     unsigned long long *ticket;  // null: tile = block index (the whole grid is resident at once)
     unsigned long long *heavy;   // ctl[0..]: count + listed rows
     int64_t *d_E;                // out: number of sampled edges of the hop
-    int n_front;                 // heavy blocks at the front of the grid (0 on hop 0: the list is still empty)
+    int n_front;                 // heavy blocks at the front of the grid = the call's list cap (0 on hop 0: the list is still empty)
     int release_early;           // the grid leaves room on every SM: the reindex kernel's blocks may become resident at once
 };
 
@@ -465,7 +473,7 @@ __global__ void __launch_bounds__(kHopThreads, kMinBlocks) hop_sample_kernel(con
 
     if (static_cast<int>(blockIdx.x) < a.n_front) {
         // ---- heavy block: one listed row's logical warp; warp 0 generates, warps 1..7 test ------------------------------
-        const unsigned long long n_listed = min(a.heavy[0], static_cast<unsigned long long>(kHeavyListCap));
+        const unsigned long long n_listed = min(a.heavy[0], static_cast<unsigned long long>(a.n_front));
         if (blockIdx.x >= n_listed) return;
         const int64_t r = static_cast<int64_t>(a.heavy[1 + blockIdx.x]);
         const int64_t b = r >> 6;
@@ -558,7 +566,7 @@ __global__ void __launch_bounds__(kHopThreads, kMinBlocks) hop_sample_kernel(con
         // does a heavy block serve this warp?  (only warps owning a listed-size row need to look)
         const bool big = lane < kRowsPerWarp && sm[ts].deg[w + kSampleWarps * lane] > kHeavyDeg;
         if (__any_sync(0xffffffffu, big)) {
-            const unsigned int n_listed = static_cast<unsigned int>(min(a.heavy[0], static_cast<unsigned long long>(kHeavyListCap)));
+            const unsigned int n_listed = static_cast<unsigned int>(min(a.heavy[0], static_cast<unsigned long long>(a.n_front)));
             bool found = false;
             for (unsigned int j = lane; j < n_listed; j += 32) {
                 const int64_t o = static_cast<int64_t>(a.heavy[1 + j]);
@@ -601,6 +609,8 @@ struct HopReindexArgs {
     const int64_t *indptr;
     int64_t *fr_start, *fr_deg;  // null on the last hop
     unsigned long long *heavy;
+    unsigned int heavy_cap;   // entries the list takes in this call (= the sampling kernels' n_front)
+    int64_t *d_heavy_seen;    // rows above kHeavyDeg seen so far in this call (listed or not): the host sizes the next call's cap
     const int32_t *tgt;
     int64_t *edge_buf;  // [col (E) | row (E)]
     unsigned long long *bar;
@@ -777,7 +787,7 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
                         a.fr_deg[local] = deg;
                         if (deg > kHeavyDeg) {
                             const unsigned long long at = atomicAdd(a.heavy, 1ull);
-                            if (at < kHeavyListCap) a.heavy[1 + at] = static_cast<unsigned long long>(local);
+                            if (at < a.heavy_cap) a.heavy[1 + at] = static_cast<unsigned long long>(local);
                         }
                     }
                 }
@@ -847,7 +857,10 @@ __global__ void __launch_bounds__(kReindexThreads, 2) hop_reindex_kernel(const _
                 base += red[0][x];
                 tot += red[1][x];
             }
-            if (lane == 0 && blockIdx.x == gridDim.x - 1) *a.d_E_next = tot;
+            if (lane == 0 && blockIdx.x == gridDim.x - 1) {
+                *a.d_E_next = tot;
+                *a.d_heavy_seen = static_cast<int64_t>(__ldcg(a.heavy));
+            }
             const int cnt = static_cast<int>(t_hi - t_lo);
             constexpr int kPer = kReindexTilesPerBlock / 32;
             long long v[kPer], sum = 0;

@@ -42,6 +42,7 @@ namespace
 constexpr int kMetaS = 0;  // number of seeds of the hop
 constexpr int kMetaE = 1;  // number of sampled edges (sum of counts)
 constexpr int kMetaF = 2;  // frontier size after reindex
+constexpr int kMetaHeavy = 3;  // fused k-hop: rows above kHeavyDeg in the frontier after the hop (sizes the next call's heavy list)
 constexpr int kMetaStride = 4;
 constexpr int kMetaWords = kMetaStride * (QV_MAX_HOPS + 1);
 
@@ -1439,6 +1440,7 @@ struct qv_sampler {
     Buffer rng_cache;  // states for rand_seed == 0, blocks [0, rng_cache_blocks)
     int64_t rng_cache_blocks = 0;
     Buffer rng_tmp;  // states for rand_seed != 0 (per launch)
+    int heavy_front = kHeavyFrontInit;  // heavy blocks in front of a fused hop's sampling grid (kHeavyFrontInit, grown on demand)
     Buffer ctl;       // control words of the two-kernels-per-hop path (heavy list, tile descriptors, barrier counters)
     Buffer tgt;       // int32[E]: target row of every sampled edge of the current hop (two-kernels-per-hop path)
     Buffer tile_base; // int64[tiles]: output offset of every 64-row tile of the next hop (written by hop_reindex_kernel)
@@ -2149,7 +2151,7 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
             a.item_base = h == 0 ? S : 0;
             a.d_err = d_err;
         }
-        a.n_front = (h == 0 || s->max_degree <= kHeavyDeg) ? 0 : kHeavyListCap;
+        a.n_front = (h == 0 || s->max_degree <= kHeavyDeg) ? 0 : s->heavy_front;
         const int64_t tiles = (bn[h] + kSampleTile - 1) / kSampleTile;
         const int64_t blocks = (tiles + kHopTiles - 1) / kHopTiles;
         const size_t smem = static_cast<size_t>(kHopWarps) * kRowsPerWarp * std::max(k, 1) * 13;
@@ -2178,6 +2180,8 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
         r.fr_start = h + 1 < n_hops ? fr_start : nullptr;
         r.fr_deg = h + 1 < n_hops ? fr_deg : nullptr;
         r.heavy = ctl;
+        r.heavy_cap = static_cast<unsigned int>(s->heavy_front);
+        r.d_heavy_seen = m + kMetaHeavy;
         r.tgt = tgt;
         r.edge_buf = edge_buf[h];
         r.bar = hop + 1;
@@ -2207,6 +2211,12 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
                               tail.row_bytes, tail.features, tail.variant, st));
     }
     QV_CUDA(cudaEventSynchronize(s->meta_ready));
+    if (n_hops >= 2) {  // more rows above kHeavyDeg than heavy blocks: the rest walked their chain in one warp; grow for the next call
+        const int64_t seen = s->h_meta[kMetaStride * (n_hops - 2) + kMetaHeavy];
+        static const bool fixed = getenv("QV_HEAVY_FRONT_FIXED") != nullptr;  // A-B switch: keep the initial cap
+        if (seen > s->heavy_front && !fixed)
+            s->heavy_front = static_cast<int>(std::min<int64_t>(kHeavyListMax, (seen + seen / 4 + 63) / 64 * 64));
+    }
     if (s->h_meta[kMetaErr] != 0) {
         *id_error = true;  // the caller redoes the call on the hash path
         s->err_dirty = true;
