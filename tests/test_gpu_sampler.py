@@ -678,3 +678,49 @@ def test_heavy_list_grows_past_its_initial_cap(oracle):
         for hop, (o_ei, _, o_pos) in zip(hops, o_adjs[::-1]):
             assert torch.equal(hop[0].cpu(), torch.from_numpy(o_ei)), it
             assert torch.equal(hop[3].cpu(), torch.from_numpy(o_pos)), it
+
+
+def test_compiled_call_path_equals_the_ctypes_path(oracle, monkeypatch):
+    """Quiver.sample_khop runs its host side compiled (csrc/pybind: khop_raw) when the adapter is built -- which build()
+    does, so on a GPU box it must be there.  Same C calls underneath: ids, edge_index, e_id and gathered rows identical to
+    the ctypes path and to the oracle; unsupported requests and bad seeds end in the same exceptions."""
+    import torch_quiver as qv
+    assert qv._compiled is not None, "the compiled call path is not built (python torch-quiver_b200/csrc/pybind/build.py)"
+    indptr, indices = powerlaw_csr(20000, 30.0, seed=31)
+    q = _quiver(indptr, indices)
+    table = torch.from_numpy(np.random.default_rng(0).integers(0, 99, (20000, 24)).astype(np.float32))
+    st = qv.ShardTensor(0)
+    st.append(table, 0)
+    order = torch.from_numpy(np.random.default_rng(1).permutation(20000)).cuda()
+    seeds = np.random.default_rng(2).permutation(20000)[:777]
+    pinned = torch.from_numpy(seeds).pin_memory()
+    sizes = [7, 5, 3]
+    o_nid, _, o_adjs = oracle.khop(indptr, indices, seeds, sizes, with_eid=True)
+
+    def run():
+        return (q.sample_khop(_dev(seeds), sizes), q.sample_khop(pinned, sizes, with_eid=True),
+                q.sample_khop(_dev(seeds), sizes, gather=(st, order)), q.sample_khop(pinned, sizes, gather=(st, None), with_eid=True))
+
+    fast = run()
+    monkeypatch.setattr(qv, "_compiled", None)
+    slow = run()
+    for f, s in zip(fast, slow):
+        assert torch.equal(f[0], s[0]) and torch.equal(f[0].cpu(), torch.from_numpy(o_nid))
+        assert len(f) == len(s) and len(f[1]) == len(s[1]) == 3
+        for hf, hs, (o_ei, _, o_pos) in zip(f[1], s[1], o_adjs[::-1]):
+            assert len(hf) == len(hs) and torch.equal(hf[0], hs[0]) and tuple(hf[1:3]) == tuple(hs[1:3])
+            assert torch.equal(hf[0].cpu(), torch.from_numpy(o_ei))
+            if len(hf) > 3:
+                assert torch.equal(hf[3], hs[3]) and torch.equal(hf[3].cpu(), torch.from_numpy(o_pos))
+        if len(f) > 2:
+            assert torch.equal(f[2], s[2])
+    assert torch.equal(fast[2][2].cpu(), table[order.cpu()[torch.from_numpy(o_nid)]])
+    assert torch.equal(fast[3][2].cpu(), table[torch.from_numpy(o_nid)])
+    monkeypatch.undo()
+    for compiled in (True, False):
+        if not compiled:
+            monkeypatch.setattr(qv, "_compiled", None)
+        with pytest.raises(qv.Unsupported):
+            q.sample_khop(_dev(seeds), [5, -1])
+        with pytest.raises(RuntimeError):
+            q.sample_khop(torch.from_numpy(seeds), sizes)  # pageable host memory is not device-visible

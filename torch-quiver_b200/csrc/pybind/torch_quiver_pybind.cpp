@@ -370,6 +370,106 @@ class ShardTensor
     std::vector<int64_t> offsets_{0};
     std::vector<Shard> shards_;
 };
+
+// ---- compiled call path of the ctypes package's fused k-hop (ours) -------------------------------------------------------
+// torch_quiver.Quiver.sample_khop (torch_quiver/__init__.py) does per call: two torch.empty, pointer tables, an 18-argument
+// ctypes call, the hop tuples.  Measured end to end that host work is the GPU's idle time between two steps,
+// so the same sequence is offered here as ONE compiled function over the SAME C objects: `sampler` is the qv_sampler* the
+// ctypes Quiver owns, `table` the address of its ShardTensor's qv_shard_table (0: no gather).  Returns None where the ctypes
+// path would raise Unsupported (the caller then takes that path and gets its error), else
+// (n_id, [(edge_index, n_src, n_dst[, e_id]) innermost hop first], x or None).
+py::object khop_raw(uintptr_t sampler, const torch::Tensor &seeds, const std::vector<int64_t> &sizes, uint64_t rand_seed, int device,
+                    int64_t node_count, uintptr_t table, const c10::optional<torch::Tensor> &feature_order, int64_t row_bytes,
+                    const std::vector<int64_t> &row_shape, at::ScalarType dtype, int variant, bool with_eid, int64_t max_bytes)
+{
+    const int n_hops = static_cast<int>(sizes.size());
+    if (n_hops < 1 || n_hops > QV_MAX_HOPS) return py::none();
+    TORCH_CHECK(seeds.scalar_type() == torch::kInt64, "seeds must be a torch.long tensor");
+    TORCH_CHECK(seeds.is_contiguous(), "seeds must be contiguous");
+    if (seeds.is_cuda()) {
+        TORCH_CHECK(seeds.get_device() == device, "seeds lives on another device than this object");
+    } else {  // pinned host memory is device-visible at the same address: hop 0 reads the seeds in place
+        TORCH_CHECK(seeds.is_pinned(), "seeds must be a CUDA tensor (or pinned host memory)");
+    }
+    const int64_t S = seeds.numel();
+    int64_t bn[QV_MAX_HOPS + 1], be[QV_MAX_HOPS];
+    if (qv_khop_bounds(S, sizes.data(), n_hops, bn, be) != QV_OK) return py::none();
+    int64_t total = (std::max<int64_t>(bn[n_hops], 1) + 1) / 2 * 2, offs[QV_MAX_HOPS], eoffs[QV_MAX_HOPS];
+    for (int h = 0; h < n_hops; h++) {
+        offs[h] = total;
+        total += std::max<int64_t>(2 * be[h], 2);
+    }
+    if (with_eid)
+        for (int h = 0; h < n_hops; h++) {
+            eoffs[h] = total;
+            total += std::max<int64_t>(be[h], 2);
+        }
+    const auto dev = torch::Device(torch::kCUDA, device);
+    int64_t x_rows = 0;
+    if (table) {
+        TORCH_CHECK(at::cuda::current_device() == device, "sample_khop(gather=...) must run with the sampler's device current");
+        x_rows = std::max<int64_t>(std::min(bn[n_hops], node_count + S), 1);
+        if (x_rows * row_bytes > max_bytes) return py::none();
+    }
+    torch::Tensor arena, x;
+    int64_t nodes[QV_MAX_HOPS + 1], edges[QV_MAX_HOPS];
+    int rc;
+    {
+        py::gil_scoped_release nogil;
+        arena = torch::empty({total}, torch::TensorOptions().dtype(torch::kInt64).device(dev));
+        int64_t *base = arena.data_ptr<int64_t>(), *bufs[QV_MAX_HOPS], *eids[QV_MAX_HOPS];
+        for (int h = 0; h < n_hops; h++) {
+            bufs[h] = base + offs[h];
+            eids[h] = with_eid ? base + eoffs[h] : nullptr;
+        }
+        const int64_t *v = seeds.data_ptr<int64_t>();
+        auto *s = reinterpret_cast<qv_sampler *>(sampler);
+        if (!table) {
+            rc = qv_khop(s, v, S, sizes.data(), n_hops, rand_seed, base, bufs, with_eid ? eids : nullptr, nodes, edges,
+                         cur_stream(device));
+        } else {
+            const int64_t *order = nullptr;
+            if (feature_order.has_value() && feature_order->defined()) order = long_ptr(*feature_order, "feature_order", device);
+            std::vector<int64_t> shape{x_rows};
+            shape.insert(shape.end(), row_shape.begin(), row_shape.end());
+            x = torch::empty(shape, torch::TensorOptions().dtype(dtype).device(dev));
+            rc = qv_khop_gather(s, v, S, sizes.data(), n_hops, rand_seed, base, bufs, with_eid ? eids : nullptr,
+                                reinterpret_cast<const qv_shard_table *>(table), order, row_bytes, x.data_ptr(), x_rows, variant,
+                                nodes, edges, cur_stream(device));
+        }
+    }
+    if (rc == QV_ERR_UNSUPPORTED) return py::none();
+    ok(rc);
+    py::list hops;
+    for (int h = 0; h < n_hops; h++) {
+        auto ei = arena.narrow(0, offs[h], 2 * edges[h]).view({2, edges[h]});
+        if (with_eid)
+            hops.append(py::make_tuple(ei, nodes[h + 1], nodes[h], arena.narrow(0, eoffs[h], edges[h])));
+        else
+            hops.append(py::make_tuple(ei, nodes[h + 1], nodes[h]));
+    }
+    if (!table) return py::make_tuple(arena.narrow(0, 0, nodes[n_hops]), hops, py::none());
+    return py::make_tuple(arena.narrow(0, 0, nodes[n_hops]), hops, x.narrow(0, 0, nodes[n_hops]));
+}
+
+// The same for ShardTensor.gather of the ctypes package: `table` = address of its qv_shard_table; returns
+// table[feature_order[indices]] on torch's current stream (qv_gather).
+torch::Tensor gather_raw(uintptr_t table, const torch::Tensor &indices, const c10::optional<torch::Tensor> &feature_order,
+                         int64_t row_bytes, const std::vector<int64_t> &row_shape, at::ScalarType dtype, int variant)
+{
+    const int device = indices.is_cuda() ? indices.get_device() : -1;
+    const int64_t *idx = long_ptr(indices, "indices", -1);
+    const int64_t *order = nullptr;
+    if (feature_order.has_value() && feature_order->defined()) order = long_ptr(*feature_order, "feature_order", device);
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(device);
+    std::vector<int64_t> shape{indices.numel()};
+    shape.insert(shape.end(), row_shape.begin(), row_shape.end());
+    auto out = torch::empty(shape, torch::TensorOptions().dtype(dtype).device(indices.device()));
+    ok(qv_gather(reinterpret_cast<const qv_shard_table *>(table), idx, order, indices.numel(), row_bytes, out.data_ptr(), variant,
+                 cur_stream(device)));
+    return out;
+}
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
@@ -412,4 +512,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
         .def("append", &ShardTensor::append_item, py::call_guard<py::gil_scoped_release>())
         .def("share_ipc", &ShardTensor::share_ipc, py::call_guard<py::gil_scoped_release>());
     m.def("abi_version", []() { return qv_abi_version(); });
+    m.def("khop_raw", &khop_raw);
+    m.def("gather_raw", &gather_raw);
 }

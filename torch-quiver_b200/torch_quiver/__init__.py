@@ -35,6 +35,33 @@ def _stream(device):
     return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _load_compiled_calls():
+    """The compiled call path of the per-step entry points (csrc/pybind/torch_quiver_pybind.cpp: khop_raw), if it is built.
+
+    Same C objects, same C calls as the ctypes code below -- only the host work around them (allocation, pointer tables,
+    argument marshalling, result tuples) runs compiled, which end to end is worth ~15 us of GPU idle time per step.
+    QUIVER_B200_COMPILED_CALLS=0 keeps everything on ctypes (A-B switch; a missing build does the same)."""
+    import importlib.util
+    import os
+    import sysconfig
+    if os.environ.get("QUIVER_B200_COMPILED_CALLS", "1") == "0":
+        return None
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "torch_quiver_pybind",
+                        "torch_quiver_pb" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if not os.path.exists(path):
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("torch_quiver_pb", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod if mod.abi_version() == lib.qv_abi_version() and hasattr(mod, "khop_raw") else None
+    except Exception:  # a stale or foreign build: the ctypes path serves every call
+        return None
+
+
+_compiled = _load_compiled_calls()
+
+
 def _ptr(t):
     return c_void_p(t.data_ptr())
 
@@ -218,6 +245,21 @@ class Quiver:
         with_eid=True: every hop tuple gains a 4th element, the e_id of its edges (CSR position or user edge id)."""
         # seeds: a CUDA tensor, or a PINNED host tensor -- pinned memory is device-visible at the same address under unified
         # addressing, so the kernels of hop 0 read the seeds straight over PCIe (8 KB) and the call needs no staging copy
+        if _compiled is not None and isinstance(seeds, torch.Tensor) and seeds.dtype == torch.int64 and seeds.is_contiguous():
+            if gather is None:
+                res = _compiled.khop_raw(self._handle.value, seeds, sizes, int(self.rand_seed), self.device, self.node_count, 0,
+                                         None, 0, (), torch.int64, 0, with_eid, 0)
+                if res is not None:
+                    return res[0], res[1]
+            else:
+                store, feature_order = gather
+                table, dtype, row_shape, row_bytes = store._gather_plan(self.device)
+                res = _compiled.khop_raw(self._handle.value, seeds, sizes, int(self.rand_seed), self.device, self.node_count,
+                                         ctypes.addressof(table), feature_order, row_bytes, row_shape, dtype,
+                                         int(store.gather_variant), with_eid, _FUSED_GATHER_MAX_BYTES)
+                if res is not None:
+                    return res
+            # None: the request is one this path does not serve -- the code below raises the matching error
         if isinstance(seeds, torch.Tensor) and not seeds.is_cuda and seeds.dtype == torch.int64 and seeds.is_pinned() \
                 and seeds.is_contiguous():
             v = seeds
@@ -544,6 +586,11 @@ class ShardTensor:
 
     def gather(self, indices, feature_order=None, out=None):
         """`self[indices]` with the optional `feature_order[idx]` indirection folded into the kernel."""
+        if _compiled is not None and out is None and isinstance(indices, torch.Tensor) and indices.is_cuda \
+                and indices.is_contiguous():
+            table, dtype, row_shape, row_bytes = self._gather_plan(indices.device.index)
+            return _compiled.gather_raw(ctypes.addressof(table), indices, feature_order, row_bytes, row_shape, dtype,
+                                        int(self.gather_variant))
         idx = _check_long_cuda(indices, "indices")
         current = idx.device.index
         n = idx.numel()
