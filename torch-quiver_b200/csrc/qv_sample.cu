@@ -2109,12 +2109,12 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
     int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start + bn[n_hops];
     // 35 KB of static + 4-53 KB of dynamic shared memory per 256-thread block: ask for the largest shared-memory carve-out
     // (with the default one ncu showed the shared-memory occupancy limit at half the register limit)
-    static unsigned long long attr_set = 0;  // per device (function attributes belong to the device's copy of the kernel)
-    if (s->device < 0 || s->device >= 64 || !(attr_set >> s->device & 1ull)) {
+    static std::atomic<unsigned long long> attr_set{0};  // per device (function attributes belong to the device's copy of the kernel)
+    if (s->device < 0 || s->device >= 64 || !(attr_set.load() >> s->device & 1ull)) {
         cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         // 35 KB static (tiles + ring) + up to 53 KB dynamic at k = 32 exceeds the 48 KB a kernel gets without opting in
         QV_CUDA(cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        if (s->device >= 0 && s->device < 64) attr_set |= 1ull << s->device;
+        if (s->device >= 0 && s->device < 64) attr_set.fetch_or(1ull << s->device);
     }
     static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 4>), kHopThreads, 0);
     for (int h = 0; h < n_hops; h++) {
