@@ -104,3 +104,21 @@ def test_xorwow_jump_ahead_equals_sequential_stepping(tmp_path):
                            os.path.join(csrc, "qv_xorwow.cu"), os.path.join(csrc, "qv_runtime.cu"), "-o", exe])
     out = subprocess.check_output([exe]).decode()
     assert "jump ok" in out
+
+
+def test_compiled_call_path_loads_and_can_be_switched_off():
+    """The ctypes package routes its per-step calls through the compiled adapter when it is built (build() builds it; this
+    test does if it is missing): the module loads without a GPU, reports the library's ABI version and exports the two call
+    shims; the A-B switch leaves the ctypes path in charge (fresh interpreters: the choice is made at import)."""
+    import sys
+    from conftest import PKG
+    subprocess.check_call([sys.executable, os.path.join(PKG, "csrc", "pybind", "build.py")], stdout=subprocess.DEVNULL)
+    code = ("import torch_quiver as qv; c = qv._compiled; "
+            "print(c is not None and c.abi_version() == qv.lib.qv_abi_version() == 2 and "
+            "all(hasattr(c, n) for n in ('khop_raw', 'gather_raw', 'Quiver', 'ShardTensor', 'ShardTensorItem')))")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(sys.path))
+    env.pop("QUIVER_B200_COMPILED_CALLS", None)
+    assert subprocess.check_output([sys.executable, "-c", code], env=env, text=True).strip() == "True"
+    code = "import torch_quiver as qv; print(qv._compiled is None)"
+    env["QUIVER_B200_COMPILED_CALLS"] = "0"
+    assert subprocess.check_output([sys.executable, "-c", code], env=env, text=True).strip() == "True"
