@@ -581,15 +581,18 @@ def run_ours(args, cfg, rank, world, local_rank):
     clocks.start()
     for b in batches_dev[:args.warmup]:
         n_id, _, adjs = sampler.sample(b)
-        feature[n_id]
+        res = feature[n_id]
     barrier()
     # The timed regions below last ~10 ms -- shorter than one nvidia-smi poll.  Keep the SAME step loop running for
-    # ~0.7 s first (untimed) so the clock / throttle record is taken under this workload's load.
+    # ~0.7 s first (untimed) so the clock / throttle record is taken under this workload's load.  Same batches, same order
+    # and the same tensor lifetimes as region A (`res` of step i-1 is alive while step i allocates): an unsplit cached block
+    # serves a request only when it is < 20 MB larger, so the allocator's cache must have seen exactly this sequence -- or a
+    # step of the per-phase region pays a cudaMalloc now and then (gather_ms_per_step 2.3 ms instead of 0.15 in one c2 run).
     t_probe = time.perf_counter()
     while time.perf_counter() - t_probe < 0.7:
         for b in timed[0]:
             n_id, _, adjs = sampler.sample(b)
-            feature[n_id]
+            res = feature[n_id]
     barrier()
 
     # ---- timed region A: K steps as the reference's two calls, inputs resident in HBM, with per-phase events -------------

@@ -2109,14 +2109,16 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
     int64_t *fr_start = static_cast<int64_t *>(s->fr_meta.ptr), *fr_deg = fr_start + bn[n_hops];
     // 35 KB of static + 4-53 KB of dynamic shared memory per 256-thread block: ask for the largest shared-memory carve-out
     // (with the default one ncu showed the shared-memory occupancy limit at half the register limit)
+    static const bool three = getenv("QV_HOP_MINB") && getenv("QV_HOP_MINB")[0] == '3';  // A-B switch: 3 resident blocks per SM
+    void (*const sample_kernel)(HopSampleArgs) = three ? hop_sample_kernel<4, 3> : hop_sample_kernel<4, 4>;
     static std::atomic<unsigned long long> attr_set{0};  // per device (function attributes belong to the device's copy of the kernel)
     if (s->device < 0 || s->device >= 64 || !(attr_set.load() >> s->device & 1ull)) {
-        cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(sample_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         // 35 KB static (tiles + ring) + up to 53 KB dynamic at k = 32 exceeds the 48 KB a kernel gets without opting in
-        QV_CUDA(cudaFuncSetAttribute(hop_sample_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        QV_CUDA(cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         if (s->device >= 0 && s->device < 64) attr_set.fetch_or(1ull << s->device);
     }
-    static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(hop_sample_kernel<4, 4>), kHopThreads, 0);
+    static const int sample_per_sm = blocks_per_sm(reinterpret_cast<const void *>(sample_kernel), kHopThreads, 0);
     for (int h = 0; h < n_hops; h++) {
         int64_t *m = s->d_meta + kMetaStride * h;
         unsigned long long *hop = ctl + kCtlHeader + stride * h;
@@ -2159,7 +2161,7 @@ int khop_run_fused(qv_sampler *s, const int64_t *seeds, int64_t S, const int64_t
         // a grid of at most ~3 blocks per SM leaves registers and threads for the reindex kernel's two 512-thread blocks
         static const bool early_off = getenv("QV_HOP_EARLY") && getenv("QV_HOP_EARLY")[0] == '0';
         a.release_early = (!early_off && blocks + a.n_front <= int64_t(3) * s->n_sm / 2) ? 1 : 0;
-        QV_CUDA(launch_chained(hop_sample_kernel<4, 4>, static_cast<unsigned>(blocks + a.n_front), kHopThreads, smem, st, a));
+        QV_CUDA(launch_chained(sample_kernel, static_cast<unsigned>(blocks + a.n_front), kHopThreads, smem, st, a));
         QV_CHECK_LAUNCH("hop_sample_kernel");
 
         HopReindexArgs r;
